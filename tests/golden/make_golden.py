@@ -1,0 +1,148 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors, so parity is pinned on
+outputs of the reference's own classes imported read-only from /root/reference through
+oracle/ref_shims.py:
+  * model-level:  models/FC_STGNN/Model.py FC_STGNN_RUL -- eval forward, train forward with
+    the positional-encoding dropout mask pinned, running statistics after one train forward,
+    d(mse)/d(param) for every parameter and dX.
+  * block-level:  models/FC_STGNN/Model_Base.py GraphConvpoolMPNN_block_v6 -- same, on random
+    [B,T,N,C] inputs, strides 1 and 2.
+Seeds follow utils.py:63-69 fix_randomness(seed) (torch.manual_seed) before construction.
+The .npz files are small (float32, tiny batches) and are committed; this script is the
+provenance record.  /root/reference does not travel to the GPU box; the fixtures do.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_shims  # noqa: E402
+from oracle.fc_stgnn_oracle import CONFIGS  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+class PinnedDropout(torch.nn.Module):
+    """Stands in for nn.Dropout(p) on a reference *instance* so the mask is reproducible."""
+
+    def __init__(self, keep, p):
+        super().__init__()
+        self.keep, self.p = keep, p
+
+    def forward(self, x):
+        if not self.training:
+            return x
+        return x * self.keep / (1.0 - self.p)
+
+
+def _np(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def perturb_bn_(module, gen):
+    """Fresh BN layers have weight=1,bias=0,mean=0,var=1 -- give them non-trivial values so
+    the goldens exercise the affine + running-stat paths."""
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            with torch.no_grad():
+                m.weight.copy_(0.5 + torch.rand(m.weight.shape, generator=gen))
+                m.bias.copy_(0.2 * torch.randn(m.bias.shape, generator=gen))
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=gen))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=gen))
+
+
+def model_golden(name, cfg, bs, seed):
+    FC_STGNN_RUL, _ = ref_shims.fc_stgnn_classes()
+    torch.manual_seed(seed)
+    model = FC_STGNN_RUL(**cfg)
+    gen = torch.Generator().manual_seed(seed + 1000)
+    perturb_bn_(model, gen)
+    N, Lraw = cfg["num_node"], cfg["num_patch"] * cfg["patch_size"]
+    X = torch.rand(bs, N, Lraw, generator=gen)
+    y = torch.rand(bs, 1, generator=gen)
+    C = 2 * cfg["hidden_dim"]
+    keep = (torch.rand(bs * N, cfg["num_patch"], C, generator=gen) >= 0.1).float()
+    model.positional_encoding.dropout = PinnedDropout(keep, 0.1)
+
+    out = {"X": _np(X), "y": _np(y), "keep": _np(keep).astype(np.uint8)}
+    for k, v in model.state_dict().items():
+        if k == "positional_encoding.pe":
+            out["pe_head"] = _np(v[0, :64])
+            continue
+        out["sd0/" + k] = _np(v)
+    model.eval()
+    with torch.no_grad():
+        out["y_eval"] = _np(model(X))
+    model.train()
+    Xg = X.clone().requires_grad_(True)
+    pred = model(Xg)
+    loss = torch.nn.functional.mse_loss(pred, y)
+    loss.backward()
+    out["y_train"] = _np(pred)
+    out["loss"] = _np(loss)
+    out["grad/X"] = _np(Xg.grad)
+    for k, p in model.named_parameters():
+        out["grad/" + k] = _np(p.grad)
+    for k, v in model.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            out["sd1/" + k] = _np(v)
+    path = os.path.join(OUT, f"model_{name}_b{bs}_s{seed}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def block_golden(tag, B, T, N, C, H, stride, seed):
+    _, Block = ref_shims.fc_stgnn_classes()
+    torch.manual_seed(seed)
+    blk = Block(C, H, N, 10, time_window_size=2, stride=stride, decay=0.7, pool_choice="mean")
+    gen = torch.Generator().manual_seed(seed + 2000)
+    perturb_bn_(blk, gen)
+    x = torch.randn(B, T, N, C, generator=gen)
+    out = {"x": _np(x), "stride": np.int64(stride)}
+    for k, v in blk.state_dict().items():
+        out["sd0/" + k] = _np(v)
+    blk.eval()
+    with torch.no_grad():
+        out["out_eval"] = _np(blk(x))
+    blk.train()
+    xg = x.clone().requires_grad_(True)
+    o = blk(xg)
+    dout = torch.randn(o.shape, generator=gen)
+    (o * dout).sum().backward()
+    out["out_train"] = _np(o)
+    out["dout"] = _np(dout)
+    out["grad/x"] = _np(xg.grad)
+    for k, p in blk.named_parameters():
+        out["grad/" + k] = _np(p.grad)
+    for k, v in blk.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            out["sd1/" + k] = _np(v)
+    out["mask"] = _np(blk.pre_relation)
+    path = os.path.join(OUT, f"block_{tag}_s{stride}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def main():
+    model_golden("FD004", CONFIGS["FD004"], 6, 0)
+    model_golden("FD004", CONFIGS["FD004"], 3, 1)
+    model_golden("FD001", CONFIGS["FD001"], 4, 0)
+    model_golden("NCMAPSS", CONFIGS["NCMAPSS"], 3, 0)
+    model_golden("S2", CONFIGS["S2"], 2, 0)
+    for stride in (1, 2):
+        block_golden("S1_B5_T25_N14_C16_H8", 5, 25, 14, 16, 8, stride, 0)     # FD004 shapes
+        block_golden("S2_B3_T50_N21_C14_H7", 3, 50, 21, 14, 7, stride, 1)     # north_star synthetic
+        block_golden("NC_B3_T25_N20_C16_H8", 3, 25, 20, 16, 8, stride, 2)     # N-CMAPSS
+        block_golden("FD3_B2_T12_N14_C48_H24", 2, 12, 14, 48, 24, stride, 3)  # FD003 widths
+        block_golden("min_B2_T2_N14_C16_H8", 2, 2, 14, 16, 8, stride, 4)      # FD001: T == w (one window)
+        block_golden("odd_B2_T7_N3_C4_H2", 2, 7, 3, 4, 2, stride, 5)          # ragged tail (T-w not /stride)
+
+
+if __name__ == "__main__":
+    main()
