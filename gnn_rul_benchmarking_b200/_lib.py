@@ -1,0 +1,86 @@
+"""ctypes binding of libstgconv_b200.so (the C ABI in include/stgconv_b200.h).
+
+There is no CPU fallback: importing this module builds the library when it is missing or
+stale (nvcc is in the image) and raises if it cannot be loaded.  Calls that need a GPU raise
+RuntimeError from the status code when none is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+c_float_p = C.POINTER(C.c_float)
+c_double_p = C.POINTER(C.c_double)
+
+
+class StgBlockDesc(C.Structure):
+    """struct stg_block_desc (include/stgconv_b200.h)."""
+    _fields_ = [
+        ("H", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32), ("decay", C.c_float),
+        ("Wm", C.c_void_p), ("bm", C.c_void_p), ("bn0_w", C.c_void_p), ("bn0_b", C.c_void_p),
+        ("bn0_rm", C.c_void_p), ("bn0_rv", C.c_void_p), ("Wt", C.c_void_p), ("bt", C.c_void_p),
+        ("bn1_w", C.c_void_p), ("bn1_b", C.c_void_p), ("bn1_rm", C.c_void_p), ("bn1_rv", C.c_void_p),
+        ("out", C.c_void_p), ("out_bstride", C.c_int64), ("yp", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+class StgBlockGrads(C.Structure):
+    """struct stg_block_grads."""
+    _fields_ = [
+        ("dout", C.c_void_p), ("dout_bstride", C.c_int64),
+        ("dWm", C.c_void_p), ("dbm", C.c_void_p), ("dbn0_w", C.c_void_p), ("dbn0_b", C.c_void_p),
+        ("dWt", C.c_void_p), ("dbt", C.c_void_p), ("dbn1_w", C.c_void_p), ("dbn1_b", C.c_void_p),
+        ("dxp", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/stgconv_b200.h declares
+SIGNATURES = {
+    "stg_last_error": (C.c_char_p, []),
+    "stg_version": (C.c_char_p, []),
+    "stg_block_xmoments": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "stg_block_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(StgBlockDesc), C.c_int,
+                                    C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "stg_block_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(StgBlockDesc),
+                                     C.POINTER(StgBlockGrads), C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Returns the loaded CDLL; builds it first if the sources changed.  Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if os.environ.get("STG_NO_BUILD") != "1":
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError(f"{_build.LIB} is missing and could not be built: the CUDA extension is required "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(_build.LIB)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class StgError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str = "") -> None:
+    if status == 0:
+        return
+    msg = load().stg_last_error().decode()
+    if status in (-1, -2):
+        raise ValueError(f"{what}: {msg} (status {status})")
+    raise StgError(f"{what}: {msg} (status {status})")

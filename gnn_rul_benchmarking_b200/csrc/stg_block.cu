@@ -1,0 +1,968 @@
+// Graph-conv block kernels (sm_100a) == GraphConvpoolMPNN_block_v6
+// (reference models/FC_STGNN/Model_Base.py:175-225; math restated in SURVEY.md section 9).
+//
+// Re-associations relative to the reference (all exact in real arithmetic):
+//   * F = Linear_map(x) and V = BN0(x).Wtheta^T are computed ONCE per (b,t,n) row -- the reference
+//     recomputes them for every window that contains the time step (unfold first, :194-201).
+//   * BN0 is folded into the theta projection: V = x.W'^T + b',  W' = Wtheta.diag(g0*r0).
+//   * theta(A.Xb) = A.(Xb.Wtheta^T) + btheta, so the aggregation runs over H (not C) features.
+//   * BN0 batch statistics come from per-time-step moments of x weighted by the number of
+//     windows covering each step (no unfolded tensor is ever materialised).
+//
+// Launch sequence (training): [xmoments] -> fwd_main<TRAIN> -> fwd_fin ;
+//                             bwd_stats -> bwd_main -> bwd_fin.     Eval: fwd_main<EVAL> only.
+#include "stg_block.cuh"
+
+#include <math.h>
+#include <stdio.h>
+
+namespace stg {
+
+namespace {
+
+STG_DEVINL int cover_count(int t, int w, int s, int L) {
+  int c = 0;
+  for (int j = 0; j < w; ++j) {
+    const int d = t - j;
+    if (d >= 0 && d % s == 0 && d / s < L) ++c;
+  }
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-(t,c) moments of x over (b,n):  xmom[t*C+c] += sum x, xmom[T*C+t*C+c] += sum x^2
+// grid (T, BCH); block 256.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_xmoments(const float* __restrict__ x, int B, int T, int N, int C,
+                                                  double* __restrict__ xmom) {
+  extern __shared__ float sm[];   // [2*C]
+  const int t = blockIdx.x;
+  const int nb = gridDim.y;
+  const int bper = (B + nb - 1) / nb;
+  const int b0 = blockIdx.y * bper, b1 = min(B, b0 + bper);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int NC = N * C;
+  for (int e = threadIdx.x; e < NC; e += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int b = b0; b < b1; ++b) {
+      const float v = x[((size_t)b * T + t) * NC + e];
+      s1 += v;
+      s2 += v * v;
+    }
+    const int c = e % C;
+    atomicAdd(&sm[c], s1);
+    atomicAdd(&sm[C + c], s2);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&xmom[t * C + c], (double)sm[c]);
+    atomicAdd(&xmom[(size_t)T * C + t * C + c], (double)sm[C + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory carve-up common to the forward / backward main kernels
+// ------------------------------------------------------------------------------------------
+template <int CP, int HP>
+struct Carve {
+  static constexpr int CPH = CP + HP;
+  uint64_t* bar;
+  float *mu0, *r0, *a0, *c0, *biasc, *bn1c, *pw, *WcT, *xs, *FV, *Sb;
+  // backward extras
+  float *WmS, *WtS, *dFV, *invs, *dYs, *red;
+  __device__ Carve(unsigned char* base, int rows_max, int C, int wpc, int slot, int M, bool bwd) {
+    bar = reinterpret_cast<uint64_t*>(base);
+    float* p = reinterpret_cast<float*>(base + 16);
+    mu0 = p; p += CP;
+    r0 = p; p += CP;
+    a0 = p; p += CP;
+    c0 = p; p += CP;
+    biasc = p; p += CPH;
+    bn1c = p; p += 8 * HP;
+    pw = p; p += 4;
+    WcT = p; p += CP * CPH;
+    xs = p; p += ((rows_max * C + 4 + 3) / 4) * 4 + 4;
+    FV = p; p += rows_max * CPH;
+    Sb = p; p += wpc * slot;
+    if (bwd) {
+      WmS = p; p += CP * CP;
+      WtS = p; p += HP * CP;
+      dFV = p; p += rows_max * CPH;
+      invs = p; p += ((wpc * M + 3) / 4) * 4;
+      dYs = p; p += wpc * M * HP;
+      red = p; p += 2 * CP + 2 * HP;
+    }
+  }
+};
+
+static size_t carve_bytes(int CP, int HP, int rows_max, int C, int wpc, int slot, int M, bool bwd) {
+  const int CPH = CP + HP;
+  size_t f = 4 * CP + CPH + 8 * HP + 4 + (size_t)CP * CPH + (((size_t)rows_max * C + 4 + 3) / 4) * 4 + 4 +
+             (size_t)rows_max * CPH + (size_t)wpc * slot;
+  if (bwd)
+    f += (size_t)CP * CP + (size_t)HP * CP + (size_t)rows_max * CPH + (((size_t)wpc * M + 3) / 4) * 4 +
+         (size_t)wpc * M * HP + 2 * CP + 2 * HP;
+  return 16 + f * 4;
+}
+
+// BN0 statistics (batch or running), folded projection [Wm | Wtheta.diag(g0 r0)]^T and biases.
+template <int CP, int HP, bool TRAIN>
+STG_DEVINL void block_prologue(const BlkArgs& a, const BlkDev& k, Carve<CP, HP>& sm, bool update_running) {
+  constexpr int CPH = CP + HP;
+  const int C = a.C, T = a.T, H = k.H, tid = threadIdx.x, nt = blockDim.x;
+  const int M = k.w * a.N;
+  if (tid < CP) {
+    const int c = tid;
+    float mean = 0.f, r = 0.f, av = 0.f, cv = 0.f;
+    if (c < C) {
+      double m, var;
+      if (TRAIN) {
+        double sum = 0.0, sq = 0.0;
+        for (int t = 0; t < T; ++t) {
+          const int cnt = cover_count(t, k.w, k.stride, k.L);
+          if (cnt) {
+            sum += cnt * a.xmom[t * C + c];
+            sq += cnt * a.xmom[(size_t)T * C + t * C + c];
+          }
+        }
+        const double R = (double)a.B * k.L * M;
+        m = sum / R;
+        var = sq / R - m * m;
+        if (var < 0.0) var = 0.0;
+        if (update_running) {
+          const double unb = R > 1.0 ? var * R / (R - 1.0) : var;
+          k.rm0[c] = (1.f - a.momentum) * k.rm0[c] + a.momentum * (float)m;
+          k.rv0[c] = (1.f - a.momentum) * k.rv0[c] + a.momentum * (float)unb;
+        }
+      } else {
+        m = k.rm0[c];
+        var = k.rv0[c];
+      }
+      mean = (float)m;
+      r = (float)(1.0 / sqrt(var + (double)a.eps));
+      av = k.g0[c] * r;
+      cv = k.b0[c] - av * mean;
+    }
+    sm.mu0[c] = mean;
+    sm.r0[c] = r;
+    sm.a0[c] = av;
+    sm.c0[c] = cv;
+  }
+  if (tid < 4) sm.pw[tid] = powf(k.decay, (float)tid);
+  __syncthreads();
+  for (int idx = tid; idx < CP * CPH; idx += nt) {
+    const int c = idx / CPH, o = idx % CPH;
+    float v = 0.f;
+    if (c < C) {
+      if (o < C) v = k.Wm[o * C + c];
+      else if (o >= CP && o - CP < H) v = k.Wt[(o - CP) * C + c] * sm.a0[c];
+    }
+    sm.WcT[idx] = v;
+  }
+  for (int o = tid; o < CPH; o += nt) {
+    float v = 0.f;
+    if (o < C) v = k.bm[o];
+    else if (o >= CP && o - CP < H) {
+      const float* wr = k.Wt + (o - CP) * C;
+      for (int c = 0; c < C; ++c) v += wr[c] * sm.c0[c];
+    }
+    sm.biasc[o] = v;
+  }
+}
+
+// FV[row][0:CP] = F = x.Wm^T + bm ; FV[row][CP:CP+HP] = V = BN0(x).Wtheta^T   (no btheta)
+template <int CP, int HP>
+STG_DEVINL void compute_fv(const Carve<CP, HP>& sm, const float* xs, int rows, int C) {
+  constexpr int CPH = CP + HP, G = CPH / 4;
+  for (int item = threadIdx.x; item < rows * G; item += blockDim.x) {
+    const int row = item / G, og = item % G;
+    float4 acc = *reinterpret_cast<const float4*>(sm.biasc + og * 4);
+    const float* xr = xs + row * C;
+    const float* wp = sm.WcT + og * 4;
+    for (int c = 0; c < C; ++c) {
+      const float xv = xr[c];
+      const float4 w4 = *reinterpret_cast<const float4*>(wp + c * CPH);
+      acc.x = fmaf(xv, w4.x, acc.x);
+      acc.y = fmaf(xv, w4.y, acc.y);
+      acc.z = fmaf(xv, w4.z, acc.z);
+      acc.w = fmaf(xv, w4.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(sm.FV + row * CPH + og * 4) = acc;
+  }
+}
+
+template <int CP>
+STG_DEVINL float dot_cp(const float (&a)[CP], const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CP; c += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(b + c);
+    s = fmaf(a[c], v.x, s);
+    s = fmaf(a[c + 1], v.y, s);
+    s = fmaf(a[c + 2], v.z, s);
+    s = fmaf(a[c + 3], v.w, s);
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward main: one CTA = (chunk of windows, sample b, block z)
+// ------------------------------------------------------------------------------------------
+template <int CP, int HP, bool TRAIN>
+__global__ void __launch_bounds__(256) k_block_fwd(const BlkArgs a, int rows_max, int wpc, int slot) {
+  constexpr int CPH = CP + HP;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const BlkDev& k = a.b[blockIdx.z];
+  const int chunk = blockIdx.x;
+  if (chunk >= k.nchunk_f) return;
+  const int b = blockIdx.y;
+  const int N = a.N, C = a.C, T = a.T, H = k.H, w = k.w, s = k.stride, L = k.L, M = w * N;
+  const int per = (L + k.nchunk_f - 1) / k.nchunk_f;
+  const int l0 = chunk * per, l1 = min(L, l0 + per);
+  if (l0 >= l1) return;
+  const int t_lo = l0 * s, t_hi = (l1 - 1) * s + w - 1;
+  const int rows = (t_hi - t_lo + 1) * N;
+  const int tid = threadIdx.x;
+
+  Carve<CP, HP> sm(smraw, rows_max, C, wpc, slot, M, false);
+  if (tid == 0) mbar_init(sm.bar, 1);
+  __syncthreads();
+  const int shift = stage_floats_tma(sm.xs, a.x + ((size_t)b * T + t_lo) * N * C, rows * C, sm.bar, tid);
+  const float* xs = sm.xs + shift;
+
+  block_prologue<CP, HP, TRAIN>(a, k, sm, chunk == 0 && b == 0);
+  // BN1 coefficients (eval only): yn = a1*y + c1
+  if (!TRAIN && tid < HP) {
+    float a1 = 0.f, c1 = 0.f;
+    if (tid < H) {
+      const float r1 = (float)(1.0 / sqrt((double)k.rv1[tid] + (double)a.eps));
+      a1 = k.g1[tid] * r1;
+      c1 = k.b1[tid] - a1 * k.rm1[tid];
+    }
+    sm.bn1c[tid] = a1;
+    sm.bn1c[HP + tid] = c1;
+  }
+  mbar_wait(sm.bar, 0);
+  __syncthreads();
+  compute_fv<CP, HP>(sm, xs, rows, C);
+  __syncthreads();
+
+  const int slot_id = tid / M, i = tid - slot_id * M;
+  const int ji = i / N;
+  const bool lane_ok = tid < wpc * M;
+  float* Sb = sm.Sb + slot_id * slot;
+  float st1[HP], st2[HP];
+#pragma unroll
+  for (int h = 0; h < HP; ++h) st1[h] = st2[h] = 0.f;
+  const float invw = 1.f / (float)w;
+
+  for (int lb = l0; lb < l1; lb += wpc) {
+    const int l = lb + slot_id;
+    const bool act = lane_ok && l < l1;
+    float y[HP];
+    if (act) {
+      const float* FVw = sm.FV + (size_t)(l * s - t_lo) * N * CPH;
+      float Fi[CP];
+#pragma unroll
+      for (int c = 0; c < CP; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(FVw + i * CPH + c);
+        Fi[c] = v.x; Fi[c + 1] = v.y; Fi[c + 2] = v.z; Fi[c + 3] = v.w;
+      }
+      float* Srow = Sb + i * (M + 1);
+      float mx = -INFINITY;
+      for (int kk = 0; kk < M; ++kk) {
+        const float sv = lrelu(dot_cp<CP>(Fi, FVw + kk * CPH));
+        Srow[kk] = sv;
+        if (kk != i) mx = fmaxf(mx, sv);
+      }
+      float acc[HP];
+#pragma unroll
+      for (int h = 0; h < HP; ++h) acc[h] = 0.f;
+      float sum = 0.f;
+      int kk = 0;
+      for (int j2 = 0; j2 < w; ++j2) {
+        const float mk = sm.pw[abs(j2 - ji)];
+        for (int n2 = 0; n2 < N; ++n2, ++kk) {
+          if (kk == i) continue;
+          const float e = __expf(Srow[kk] - mx);
+          sum += e;
+          const float em = e * mk;
+          const float* Vk = FVw + kk * CPH + CP;
+#pragma unroll
+          for (int h = 0; h < HP; h += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(Vk + h);
+            acc[h] = fmaf(em, v.x, acc[h]);
+            acc[h + 1] = fmaf(em, v.y, acc[h + 1]);
+            acc[h + 2] = fmaf(em, v.z, acc[h + 2]);
+            acc[h + 3] = fmaf(em, v.w, acc[h + 3]);
+          }
+        }
+      }
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      const float* Vi = FVw + i * CPH + CP;
+#pragma unroll
+      for (int h = 0; h < HP; ++h) y[h] = (h < H) ? fmaf(acc[h], inv, Vi[h] + k.bt[h]) : 0.f;
+      if (TRAIN) {
+        float* yrow = k.yp + (((size_t)b * L + l) * M + i) * H;
+#pragma unroll
+        for (int h = 0; h < HP; ++h)
+          if (h < H) {
+            yrow[h] = y[h];
+            st1[h] += y[h];
+            st2[h] = fmaf(y[h], y[h], st2[h]);
+          }
+      }
+    }
+    if (!TRAIN) {
+      // BN1 (running stats) + leaky_relu + mean over the w rows of each sensor
+      __syncthreads();
+      if (act) {
+#pragma unroll
+        for (int h = 0; h < HP; ++h) Sb[i * HP + h] = lrelu(fmaf(sm.bn1c[h], y[h], sm.bn1c[HP + h]));
+      }
+      __syncthreads();
+      if (act) {
+        float* orow = k.out + (size_t)b * k.out_bs + (size_t)l * N * H;
+        for (int e = i; e < N * H; e += M) {
+          const int n = e / H, h = e - n * H;
+          float v = 0.f;
+          for (int j = 0; j < w; ++j) v += Sb[(j * N + n) * HP + h];
+          orow[e] = v * invw;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (TRAIN) {
+    // CTA-level reduction of the BN1 moments, then one double atomic per feature
+    __syncthreads();
+    float* red = sm.Sb;   // reuse
+    if (tid < 2 * HP) red[tid] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < HP; ++h) {
+      const float v1 = warp_sum(st1[h]), v2 = warp_sum(st2[h]);
+      if ((tid & 31) == 0) {
+        atomicAdd(&red[h], v1);
+        atomicAdd(&red[HP + h], v2);
+      }
+    }
+    __syncthreads();
+    if (tid < H) {
+      atomicAdd(&k.stats[tid], (double)red[tid]);
+      atomicAdd(&k.stats[H + tid], (double)red[HP + tid]);
+    }
+  }
+}
+
+// BN1 batch-stat coefficients from the accumulated moments. tid < H computes; result in smem c[]:
+//   c[0*HP+h]=a1  c[1*HP+h]=c1  c[2*HP+h]=mu1  c[3*HP+h]=r1
+STG_DEVINL void bn1_coeffs(const BlkArgs& a, const BlkDev& k, float* c, int HPs, bool update_running) {
+  const int h = threadIdx.x;
+  if (h < k.H) {
+    const double R = (double)a.B * k.L * k.w * a.N;
+    const double m = k.stats[h] / R;
+    double var = k.stats[k.H + h] / R - m * m;
+    if (var < 0.0) var = 0.0;
+    const float r1 = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float a1 = k.g1[h] * r1;
+    c[h] = a1;
+    c[HPs + h] = k.b1[h] - a1 * (float)m;
+    c[2 * HPs + h] = (float)m;
+    c[3 * HPs + h] = r1;
+    if (update_running) {
+      const double unb = R > 1.0 ? var * R / (R - 1.0) : var;
+      k.rm1[h] = (1.f - a.momentum) * k.rm1[h] + a.momentum * (float)m;
+      k.rv1[h] = (1.f - a.momentum) * k.rv1[h] + a.momentum * (float)unb;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward finalize (training): out = mean_j lrelu(BN1(Y'))        grid (ceil(B*L*N*H/256), 1, nblk)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_block_fwd_fin(const BlkArgs a) {
+  __shared__ float c[4 * 64];
+  const BlkDev& k = a.b[blockIdx.z];
+  const int H = k.H, N = a.N, L = k.L, w = k.w, M = w * N;
+  const long long total = (long long)a.B * L * N * H;
+  if ((long long)blockIdx.x * blockDim.x >= total) return;
+  bn1_coeffs(a, k, c, 64, blockIdx.x == 0);
+  __syncthreads();
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int h = (int)(e % H);
+  const long long r = e / H;           // (b*L + l)*N + n
+  const int n = (int)(r % N);
+  const long long bl = r / N;
+  const int l = (int)(bl % L);
+  const long long b = bl / L;
+  const float a1 = c[h], c1 = c[64 + h];
+  const float* yp = k.yp + ((size_t)bl * M + n) * H + h;
+  float v = 0.f;
+  for (int j = 0; j < w; ++j) v += lrelu(fmaf(a1, yp[(size_t)j * N * H], c1));
+  k.out[(size_t)b * k.out_bs + ((size_t)l * N + n) * H + h] = v / (float)w;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward stats: sum_R dYn, sum_R dYn*Yhat per h.   grid (nCTA, 1, nblk), thread per row (b,l,m)
+// ------------------------------------------------------------------------------------------
+template <int HP>
+__global__ void __launch_bounds__(256) k_block_bwd_stats(const BlkArgs a) {
+  __shared__ float c[4 * 64];
+  __shared__ float red[2 * HP];
+  const BlkDev& k = a.b[blockIdx.z];
+  const int H = k.H, N = a.N, L = k.L, w = k.w, M = w * N;
+  bn1_coeffs(a, k, c, 64, false);
+  if (threadIdx.x < 2 * HP) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long rows = (long long)a.B * L * M;
+  float s1[HP], s2[HP];
+#pragma unroll
+  for (int h = 0; h < HP; ++h) s1[h] = s2[h] = 0.f;
+  const float invw = 1.f / (float)w;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(r % M);
+    const long long bl = r / M;
+    const int l = (int)(bl % L);
+    const long long b = bl / L;
+    const int n = m % N;
+    const float* y = k.yp + (size_t)r * H;
+    const float* d = k.dout + (size_t)b * k.dout_bs + ((size_t)l * N + n) * H;
+#pragma unroll
+    for (int h = 0; h < HP; ++h)
+      if (h < H) {
+        const float yv = y[h];
+        const float yn = fmaf(c[h], yv, c[64 + h]);
+        const float dyn = d[h] * invw * lrelu_grad(yn);
+        s1[h] += dyn;
+        s2[h] = fmaf(dyn, (yv - c[128 + h]) * c[192 + h], s2[h]);
+      }
+  }
+#pragma unroll
+  for (int h = 0; h < HP; ++h) {
+    const float v1 = warp_sum(s1[h]), v2 = warp_sum(s2[h]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&red[h], v1);
+      atomicAdd(&red[HP + h], v2);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < H) {
+    atomicAdd(&k.stats[2 * H + threadIdx.x], (double)red[threadIdx.x]);
+    atomicAdd(&k.stats[3 * H + threadIdx.x], (double)red[HP + threadIdx.x]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward main: one CTA = (chunk of time steps [ta,tb), sample b, block z)
+// ------------------------------------------------------------------------------------------
+template <int CP, int HP>
+__global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max, int wpc, int slot) {
+  constexpr int CPH = CP + HP;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const BlkDev& k = a.b[blockIdx.z];
+  const int chunk = blockIdx.x;
+  if (chunk >= k.nchunk_b) return;
+  const int b = blockIdx.y;
+  const int N = a.N, C = a.C, T = a.T, H = k.H, w = k.w, s = k.stride, L = k.L, M = w * N;
+  int per = (T + k.nchunk_b - 1) / k.nchunk_b;
+  per = ((per + s - 1) / s) * s;                       // chunk boundaries on window starts
+  const int ta = chunk * per, tb = min(T, ta + per);
+  if (ta >= tb) return;
+  // windows touching [ta,tb):  l*s <= tb-1  and  l*s + w-1 >= ta
+  int l_lo = ta - (w - 1);
+  l_lo = l_lo <= 0 ? 0 : (l_lo + s - 1) / s;
+  int l_hi = min(L - 1, (tb - 1) / s);
+  const bool any_win = l_lo <= l_hi;
+  const int t_lo = any_win ? min(ta, l_lo * s) : ta;
+  const int t_hi = any_win ? max(tb - 1, l_hi * s + w - 1) : tb - 1;
+  const int rows = (t_hi - t_lo + 1) * N;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  Carve<CP, HP> sm(smraw, rows_max, C, wpc, slot, M, true);
+  if (tid == 0) mbar_init(sm.bar, 1);
+  __syncthreads();
+  const int shift = stage_floats_tma(sm.xs, a.x + ((size_t)b * T + t_lo) * N * C, rows * C, sm.bar, tid);
+  const float* xs = sm.xs + shift;
+
+  block_prologue<CP, HP, true>(a, k, sm, false);
+  // raw Wm [o][c] and Wtheta [h][c] for the transposed products
+  for (int idx = tid; idx < CP * CP; idx += nt) {
+    const int o = idx / CP, c = idx % CP;
+    sm.WmS[idx] = (o < C && c < C) ? k.Wm[o * C + c] : 0.f;
+  }
+  for (int idx = tid; idx < HP * CP; idx += nt) {
+    const int h = idx / CP, c = idx % CP;
+    sm.WtS[idx] = (h < H && c < C) ? k.Wt[h * C + c] : 0.f;
+  }
+  // BN1 backward coefficients: bn1c[0]=a1 [1]=c1 [2]=mu1 [3]=r1 [4]=g1*r1 [5]=q1 [6]=q2
+  if (tid < HP) {
+    float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (tid < H) {
+      const int h = tid;
+      const double R = (double)a.B * L * M;
+      const double m = k.stats[h] / R;
+      double var = k.stats[H + h] / R - m * m;
+      if (var < 0.0) var = 0.0;
+      const float r1 = (float)(1.0 / sqrt(var + (double)a.eps));
+      const float g1 = k.g1[h];
+      v[0] = g1 * r1;
+      v[1] = k.b1[h] - v[0] * (float)m;
+      v[2] = (float)m;
+      v[3] = r1;
+      v[4] = g1 * r1;
+      v[5] = (float)(g1 * k.stats[2 * H + h] / R) * r1;
+      v[6] = (float)(g1 * k.stats[3 * H + h] / R) * r1;
+    }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) sm.bn1c[q * HP + tid] = v[q];
+  }
+  for (int idx = tid; idx < rows * CPH; idx += nt) sm.dFV[idx] = 0.f;
+  for (int idx = tid; idx < 2 * CP + 2 * HP; idx += nt) sm.red[idx] = 0.f;
+  mbar_wait(sm.bar, 0);
+  __syncthreads();
+  compute_fv<CP, HP>(sm, xs, rows, C);
+  __syncthreads();
+
+  const int slot_id = tid / M, i = tid - slot_id * M;
+  const int ji = i / N, ni = i - ji * N;
+  const bool lane_ok = tid < wpc * M;
+  float* Sb = sm.Sb + slot_id * slot;
+  float* invs = sm.invs + slot_id * M;
+  float* dYs = sm.dYs + (size_t)slot_id * M * HP;
+  const float invw = 1.f / (float)w;
+  float dbt_acc[HP];
+#pragma unroll
+  for (int h = 0; h < HP; ++h) dbt_acc[h] = 0.f;
+
+  if (any_win)
+    for (int lb = l_lo; lb <= l_hi; lb += wpc) {
+      const int l = lb + slot_id;
+      const bool act = lane_ok && l <= l_hi;
+      const float* FVw = sm.FV + (size_t)(act ? (l * s - t_lo) : 0) * N * CPH;
+      float* Srow = Sb + i * (M + 1);
+      float dY[HP];
+      float inv = 0.f, rs = 0.f;
+      if (act) {
+        const float* yrow = k.yp + (((size_t)b * L + l) * M + i) * H;
+        const float* drow = k.dout + (size_t)b * k.dout_bs + ((size_t)l * N + ni) * H;
+        const bool own_win = (l * s >= ta) && (l * s < tb);
+#pragma unroll
+        for (int h = 0; h < HP; ++h) {
+          float v = 0.f;
+          if (h < H) {
+            const float yv = yrow[h];
+            const float yn = fmaf(sm.bn1c[h], yv, sm.bn1c[HP + h]);
+            const float dyn = drow[h] * invw * lrelu_grad(yn);
+            const float yh = (yv - sm.bn1c[2 * HP + h]) * sm.bn1c[3 * HP + h];
+            v = sm.bn1c[4 * HP + h] * dyn - sm.bn1c[5 * HP + h] - yh * sm.bn1c[6 * HP + h];
+            if (own_win) dbt_acc[h] += v;
+          }
+          dY[h] = v;
+          dYs[i * HP + h] = v;
+        }
+        float Fi[CP];
+#pragma unroll
+        for (int c = 0; c < CP; c += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(FVw + i * CPH + c);
+          Fi[c] = v.x; Fi[c + 1] = v.y; Fi[c + 2] = v.z; Fi[c + 3] = v.w;
+        }
+        float mx = -INFINITY;
+        for (int kk = 0; kk < M; ++kk) {
+          const float sv = lrelu(dot_cp<CP>(Fi, FVw + kk * CPH));
+          Srow[kk] = sv;
+          if (kk != i) mx = fmaxf(mx, sv);
+        }
+        float sum = 0.f;
+        int kk = 0;
+        for (int j2 = 0; j2 < w; ++j2) {
+          const float mk = sm.pw[abs(j2 - ji)];
+          for (int n2 = 0; n2 < N; ++n2, ++kk) {
+            if (kk == i) { Srow[kk] = 0.f; continue; }
+            const float sv = Srow[kk];
+            const float e = __expf(sv - mx);
+            sum += e;
+            const float* Vk = FVw + kk * CPH + CP;
+            float dA = 0.f;
+#pragma unroll
+            for (int h = 0; h < HP; ++h) dA = fmaf(dY[h], Vk[h], dA);
+            rs = fmaf(e * mk, dA, rs);
+            Srow[kk] = sv > 0.f ? e : -e;
+          }
+        }
+        inv = sum > 0.f ? 1.f / sum : 0.f;
+        rs *= inv;
+        invs[i] = inv;
+      }
+      __syncthreads();
+      // dV_k = sum_i A[i][k] dY'_i   (this thread plays column k = i)
+      float dV[HP];
+#pragma unroll
+      for (int h = 0; h < HP; ++h) dV[h] = 0.f;
+      if (act) {
+        int i2 = 0;
+        for (int j2 = 0; j2 < w; ++j2) {
+          const float mk = sm.pw[abs(j2 - ji)];
+          for (int n2 = 0; n2 < N; ++n2, ++i2) {
+            float p = fabsf(Sb[i2 * (M + 1) + i]) * invs[i2];
+            if (i2 == i) p += 1.f;
+            p *= mk;
+            const float* dy2 = dYs + i2 * HP;
+#pragma unroll
+            for (int h = 0; h < HP; ++h) dV[h] = fmaf(p, dy2[h], dV[h]);
+          }
+        }
+      }
+      __syncthreads();
+      // dS in place (row i)
+      if (act) {
+        int kk = 0;
+        for (int j2 = 0; j2 < w; ++j2) {
+          const float mk = sm.pw[abs(j2 - ji)];
+          for (int n2 = 0; n2 < N; ++n2, ++kk) {
+            if (kk == i) continue;
+            const float ev = Srow[kk];
+            const float P = fabsf(ev) * inv;
+            const float* Vk = FVw + kk * CPH + CP;
+            float dA = 0.f;
+#pragma unroll
+            for (int h = 0; h < HP; ++h) dA = fmaf(dY[h], Vk[h], dA);
+            const float dLam = P * (dA * mk - rs);
+            Srow[kk] = dLam * (ev > 0.f ? 1.f : kLeaky);
+          }
+        }
+      }
+      __syncthreads();
+      float dF[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) dF[c] = 0.f;
+      if (act) {
+        for (int kk = 0; kk < M; ++kk) {
+          const float g = Srow[kk] + Sb[kk * (M + 1) + i];
+          const float* Fk = FVw + kk * CPH;
+#pragma unroll
+          for (int c = 0; c < CP; c += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(Fk + c);
+            dF[c] = fmaf(g, v.x, dF[c]);
+            dF[c + 1] = fmaf(g, v.y, dF[c + 1]);
+            dF[c + 2] = fmaf(g, v.z, dF[c + 2]);
+            dF[c + 3] = fmaf(g, v.w, dF[c + 3]);
+          }
+        }
+      }
+      // fold into the per-time-step accumulators, one window offset at a time (no races)
+      for (int jj = 0; jj < w; ++jj) {
+        if (act && ji == jj) {
+          float* dst = sm.dFV + ((size_t)(l * s - t_lo) * N + i) * CPH;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) dst[c] += dF[c];
+#pragma unroll
+          for (int h = 0; h < HP; ++h) dst[CP + h] += dV[h];
+        }
+        __syncthreads();
+      }
+    }
+  __syncthreads();
+
+  // ---- owned rows: dx partial + BN0 backward sums
+  const int r_beg = (ta - t_lo) * N, r_end = (tb - t_lo) * N;
+  {
+    const int c = tid % CP, rg = tid / CP, nrg = nt / CP;
+    float sb = 0.f, sg = 0.f;
+    if (rg < nrg && c < C) {
+      float* dxp = k.dxp + ((size_t)b * T + ta) * N * C;
+      for (int r = r_beg + rg; r < r_end; r += nrg) {
+        const float* d = sm.dFV + (size_t)r * CPH;
+        float pF = 0.f, dXb = 0.f;
+        for (int o = 0; o < C; ++o) pF = fmaf(d[o], sm.WmS[o * CP + c], pF);
+#pragma unroll
+        for (int h = 0; h < HP; ++h) dXb = fmaf(d[CP + h], sm.WtS[h * CP + c], dXb);
+        const float xh = (xs[r * C + c] - sm.mu0[c]) * sm.r0[c];
+        sb += dXb;
+        sg = fmaf(dXb, xh, sg);
+        dxp[(size_t)(r - r_beg) * C + c] = fmaf(dXb, sm.a0[c], pF);
+      }
+      atomicAdd(&sm.red[c], sb);
+      atomicAdd(&sm.red[CP + c], sg);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < HP; ++h) {
+    const float v = warp_sum(dbt_acc[h]);
+    if ((tid & 31) == 0 && h < H) atomicAdd(&sm.red[2 * CP + h], v);
+  }
+  // ---- parameter gradients: G[o][c] = sum_rows dFV[r][o]*x[r][c],  so[o] = sum_rows dFV[r][o]
+  for (int idx = tid; idx < CPH * C; idx += nt) {
+    const int o = idx / C, c = idx - o * C;
+    const bool isF = o < C, isV = (o >= CP && o - CP < H);
+    if (!isF && !isV) continue;
+    float g = 0.f, so = 0.f;
+    for (int r = r_beg; r < r_end; ++r) {
+      const float d = sm.dFV[(size_t)r * CPH + o];
+      g = fmaf(d, xs[r * C + c], g);
+      so += d;
+    }
+    if (isF) {
+      atomicAdd(&k.dWm[o * C + c], g);
+      if (c == 0) atomicAdd(&k.dbm[o], so);
+    } else {
+      atomicAdd(&k.dWt[(o - CP) * C + c], fmaf(sm.a0[c], g, sm.c0[c] * so));
+    }
+  }
+  __syncthreads();
+  if (tid < C) {
+    atomicAdd(&k.stats[4 * H + tid], (double)sm.red[tid]);
+    atomicAdd(&k.stats[4 * H + C + tid], (double)sm.red[CP + tid]);
+  }
+  if (tid < H) atomicAdd(&k.dbt[tid], sm.red[2 * CP + tid]);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward finalize: dx = sum_blk dxp_blk - r0*cnt(t)*(m1 + Xhat*m2); BN affine grads.
+// grid (ceil(B*T*N*C/256)); dynamic smem: nblk * (4*C + T) floats
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_block_bwd_fin(const BlkArgs a) {
+  extern __shared__ float smf[];
+  const int C = a.C, T = a.T, N = a.N;
+  const int per = 4 * C + T;
+  for (int z = 0; z < a.nblk; ++z) {
+    const BlkDev& k = a.b[z];
+    float* tb = smf + z * per;
+    const int M = k.w * N;
+    const double R = (double)a.B * k.L * M;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double sum = 0.0, sq = 0.0;
+      for (int t = 0; t < T; ++t) {
+        const int cnt = cover_count(t, k.w, k.stride, k.L);
+        if (cnt) {
+          sum += cnt * a.xmom[t * C + c];
+          sq += cnt * a.xmom[(size_t)T * C + t * C + c];
+        }
+      }
+      const double m = sum / R;
+      double var = sq / R - m * m;
+      if (var < 0.0) var = 0.0;
+      const float r0 = (float)(1.0 / sqrt(var + (double)a.eps));
+      const float g0 = k.g0[c];
+      const double sb = k.stats[4 * k.H + c], sg = k.stats[4 * k.H + C + c];
+      tb[c] = (float)m;
+      tb[C + c] = r0;
+      tb[2 * C + c] = r0 * (float)(g0 * sb / R);
+      tb[3 * C + c] = r0 * (float)(g0 * sg / R);
+      if (blockIdx.x == 0) {
+        k.db0[c] += (float)sb;
+        k.dg0[c] += (float)sg;
+      }
+    }
+    for (int t = threadIdx.x; t < T; t += blockDim.x) tb[4 * C + t] = (float)cover_count(t, k.w, k.stride, k.L);
+    if (blockIdx.x == 0)
+      for (int h = threadIdx.x; h < k.H; h += blockDim.x) {
+        k.db1[h] += (float)k.stats[2 * k.H + h];
+        k.dg1[h] += (float)k.stats[3 * k.H + h];
+      }
+  }
+  __syncthreads();
+  const long long total = (long long)a.B * T * N * C;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int c = (int)(e % C);
+  const int t = (int)((e / ((long long)N * C)) % T);
+  const float xv = a.x[e];
+  float v = 0.f;
+  for (int z = 0; z < a.nblk; ++z) {
+    const float* tb = smf + z * per;
+    const float xh = (xv - tb[c]) * tb[C + c];
+    v += a.b[z].dxp[e] - tb[4 * C + t] * (tb[2 * C + c] + xh * tb[3 * C + c]);
+  }
+  a.dx[e] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: template dispatch + launch plan
+// ------------------------------------------------------------------------------------------
+struct Variant {
+  int CP, HP;
+  void (*fwd_train)(const BlkArgs, int, int, int);
+  void (*fwd_eval)(const BlkArgs, int, int, int);
+  void (*bwd)(const BlkArgs, int, int, int);
+  void (*bwd_stats)(const BlkArgs);
+};
+#define STG_VARIANT(CP, HP) \
+  { CP, HP, k_block_fwd<CP, HP, true>, k_block_fwd<CP, HP, false>, k_block_bwd<CP, HP>, k_block_bwd_stats<HP> }
+static const Variant kVariants[] = {
+    STG_VARIANT(4, 4), STG_VARIANT(8, 4), STG_VARIANT(16, 8), STG_VARIANT(32, 16), STG_VARIANT(48, 24),
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr size_t kSmemCap = 200 * 1024;
+
+static const Variant* pick_variant(int C, int H) {
+  for (int i = 0; i < kNumVariants; ++i)
+    if (kVariants[i].CP >= C && kVariants[i].HP >= H) return &kVariants[i];
+  return nullptr;
+}
+
+static bool g_attr_done[64] = {};
+static void set_smem_attrs() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (g_attr_done[dev]) return;
+  for (int i = 0; i < kNumVariants; ++i) {
+    cudaFuncSetAttribute(kVariants[i].fwd_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
+    cudaFuncSetAttribute(kVariants[i].fwd_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
+    cudaFuncSetAttribute(kVariants[i].bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap);
+  }
+  g_attr_done[dev] = true;
+}
+
+}  // namespace
+
+int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
+  if (a.nblk < 1 || a.nblk > 2) { snprintf(err, errlen, "nblk must be 1 or 2"); return -1; }
+  int Hmax = 0, Mmax = 0;
+  for (int z = 0; z < a.nblk; ++z) {
+    BlkDev& k = a.b[z];
+    if (k.w < 1 || k.w > kMaxWin || k.stride < 1 || a.T < k.w) {
+      snprintf(err, errlen, "unsupported window %d / stride %d for T=%d", k.w, k.stride, a.T);
+      return -2;
+    }
+    k.L = (a.T - k.w) / k.stride + 1;
+    if (k.H > 64) { snprintf(err, errlen, "hidden_dim %d > 64 unsupported", k.H); return -2; }
+    Hmax = k.H > Hmax ? k.H : Hmax;
+    Mmax = k.w * a.N > Mmax ? k.w * a.N : Mmax;
+  }
+  if (a.nblk == 2 && a.b[0].w * a.N != a.b[1].w * a.N) {
+    snprintf(err, errlen, "blocks fused in one launch must share the window size"); return -2;
+  }
+  const Variant* v = pick_variant(a.C, Hmax);
+  if (!v) { snprintf(err, errlen, "no kernel variant for C=%d H=%d (max C 48, H 24)", a.C, Hmax); return -2; }
+  const int M = Mmax;
+  if (M > 256) { snprintf(err, errlen, "w*N=%d nodes per graph > 256 unsupported", M); return -2; }
+  p.CP = v->CP; p.HP = v->HP;
+  const int slot = (M * (M + 1) > M * v->HP ? M * (M + 1) : M * v->HP);
+  int wpc = 256 / M; if (wpc < 1) wpc = 1;
+  // ---- forward: windows per chunk == windows in flight unless shared memory says otherwise
+  for (int wp = wpc; wp >= 1; --wp) {
+    int rows_max = 0, gx = 0;
+    for (int z = 0; z < a.nblk; ++z) {
+      BlkDev& k = a.b[z];
+      k.nchunk_f = (k.L + wp - 1) / wp;
+      const int per = (k.L + k.nchunk_f - 1) / k.nchunk_f;
+      const int rows = ((per - 1) * k.stride + k.w) * a.N;
+      rows_max = rows > rows_max ? rows : rows_max;
+      gx = k.nchunk_f > gx ? k.nchunk_f : gx;
+    }
+    const size_t sm = carve_bytes(v->CP, v->HP, rows_max, a.C, wp, slot, M, false);
+    if (sm <= kSmemCap || wp == 1) {
+      if (sm > kSmemCap) { snprintf(err, errlen, "forward tile does not fit shared memory (%zu B)", sm); return -2; }
+      p.wpc_f = wp; p.smem_f = sm; p.grid_x_f = gx; p.threads_f = ((wp * M + 31) / 32) * 32;
+      break;
+    }
+  }
+  // ---- backward: time steps per chunk so that the touching windows fit one pass
+  for (int wp = wpc; wp >= 1; --wp) {
+    int rows_max = 0, gx = 0;
+    for (int z = 0; z < a.nblk; ++z) {
+      BlkDev& k = a.b[z];
+      int per = wp * k.stride - (k.w - 1);
+      if (per < k.stride) per = k.stride;
+      per = (per / k.stride) * k.stride;
+      k.nchunk_b = (a.T + per - 1) / per;
+      int per2 = (a.T + k.nchunk_b - 1) / k.nchunk_b;
+      per2 = ((per2 + k.stride - 1) / k.stride) * k.stride;
+      // worst-case staged time range: owned steps plus halo windows on both sides
+      const int span = per2 + 2 * (k.w - 1) + k.stride;
+      const int rows = (span < a.T ? span : a.T) * a.N;
+      rows_max = rows > rows_max ? rows : rows_max;
+      gx = k.nchunk_b > gx ? k.nchunk_b : gx;
+    }
+    const size_t sm = carve_bytes(v->CP, v->HP, rows_max, a.C, wp, slot, M, true);
+    if (sm <= kSmemCap || wp == 1) {
+      if (sm > kSmemCap) { snprintf(err, errlen, "backward tile does not fit shared memory (%zu B)", sm); return -2; }
+      p.wpc_b = wp; p.smem_b = sm; p.grid_x_b = gx; p.threads_b = ((wp * M + 31) / 32) * 32;
+      break;
+    }
+  }
+  return 0;
+}
+
+static int rows_max_fwd(const BlkArgs& a) {
+  int rm = 0;
+  for (int z = 0; z < a.nblk; ++z) {
+    const BlkDev& k = a.b[z];
+    const int per = (k.L + k.nchunk_f - 1) / k.nchunk_f;
+    const int rows = ((per - 1) * k.stride + k.w) * a.N;
+    rm = rows > rm ? rows : rm;
+  }
+  return rm;
+}
+static int rows_max_bwd(const BlkArgs& a) {
+  int rm = 0;
+  for (int z = 0; z < a.nblk; ++z) {
+    const BlkDev& k = a.b[z];
+    int per2 = (a.T + k.nchunk_b - 1) / k.nchunk_b;
+    per2 = ((per2 + k.stride - 1) / k.stride) * k.stride;
+    const int span = per2 + 2 * (k.w - 1) + k.stride;
+    const int rows = (span < a.T ? span : a.T) * a.N;
+    rm = rows > rm ? rows : rm;
+  }
+  return rm;
+}
+
+int launch_xmoments(const float* x, int B, int T, int N, int C, double* xmom, cudaStream_t s) {
+  cudaMemsetAsync(xmom, 0, sizeof(double) * 2 * T * C, s);
+  int nb = (B + 15) / 16;
+  if (nb > 64) nb = 64;
+  k_xmoments<<<dim3(T, nb), 256, 2 * C * sizeof(float), s>>>(x, B, T, N, C, xmom);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
+  set_smem_attrs();
+  const Variant* v = pick_variant(p.CP, p.HP);
+  const int M = a.b[0].w * a.N;
+  const int slot = (M * (M + 1) > M * p.HP ? M * (M + 1) : M * p.HP);
+  const int rows_max = rows_max_fwd(a);
+  dim3 grid(p.grid_x_f, a.B, a.nblk);
+  if (a.training) {
+    for (int z = 0; z < a.nblk; ++z)
+      cudaMemsetAsync(a.b[z].stats, 0, sizeof(double) * (4 * a.b[z].H + 2 * a.C), s);
+    v->fwd_train<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max, p.wpc_f, slot);
+    long long tot = 0;
+    for (int z = 0; z < a.nblk; ++z) {
+      const long long t = (long long)a.B * a.b[z].L * a.N * a.b[z].H;
+      tot = t > tot ? t : tot;
+    }
+    k_block_fwd_fin<<<dim3((unsigned)((tot + 255) / 256), 1, a.nblk), 256, 0, s>>>(a);
+  } else {
+    v->fwd_eval<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max, p.wpc_f, slot);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
+  set_smem_attrs();
+  const Variant* v = pick_variant(p.CP, p.HP);
+  const int M = a.b[0].w * a.N;
+  const int slot = (M * (M + 1) > M * p.HP ? M * (M + 1) : M * p.HP);
+  const int rows_max = rows_max_bwd(a);
+  for (int z = 0; z < a.nblk; ++z)
+    cudaMemsetAsync(a.b[z].stats + 2 * a.b[z].H, 0, sizeof(double) * (2 * a.b[z].H + 2 * a.C), s);
+  long long rows = 0;
+  for (int z = 0; z < a.nblk; ++z) {
+    const long long r = (long long)a.B * a.b[z].L * M;
+    rows = r > rows ? r : rows;
+  }
+  int g = (int)((rows + 255) / 256);
+  if (g > 592) g = 592;
+  v->bwd_stats<<<dim3(g, 1, a.nblk), 256, 0, s>>>(a);
+  v->bwd<<<dim3(p.grid_x_b, a.B, a.nblk), p.threads_b, p.smem_b, s>>>(a, rows_max, p.wpc_b, slot);
+  const long long tot = (long long)a.B * a.T * a.N * a.C;
+  k_block_bwd_fin<<<(unsigned)((tot + 255) / 256), 256, a.nblk * (4 * a.C + a.T) * sizeof(float), s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+}  // namespace stg

@@ -1,0 +1,53 @@
+// Kernel-side argument structs of the graph-conv block kernels (stg_block.cu) shared with the
+// C-ABI layer (stg_capi.cu) and the whole-model engine (stg_engine.cu).
+#pragma once
+#include "stg_common.cuh"
+
+namespace stg {
+
+struct BlkDev {
+  int H, w, stride, L;
+  int nchunk_f;     // forward: chunks of windows per sample
+  int nchunk_b;     // backward: chunks of time steps per sample
+  float decay;
+  const float *Wm, *bm, *g0, *b0, *Wt, *bt, *g1, *b1;
+  float *rm0, *rv0, *rm1, *rv1;
+  float* out;
+  long long out_bs;
+  float* yp;
+  double* stats;
+  // backward only
+  const float* dout;
+  long long dout_bs;
+  float *dWm, *dbm, *dg0, *db0, *dWt, *dbt, *dg1, *db1, *dxp;
+};
+
+struct BlkArgs {
+  BlkDev b[2];
+  int nblk;
+  const float* x;
+  int B, T, N, C;
+  const double* xmom;   // [2][T][C] sums / sums of squares over (b,n); training only
+  float* dx;            // backward finalize output
+  int training;
+  float momentum, eps;
+};
+
+struct BlkPlan {
+  int CP, HP;           // padded feature dims the kernel template is instantiated for
+  int threads_f, threads_b;
+  int wpc_f, wpc_b;     // windows processed concurrently per CTA
+  size_t smem_f, smem_b;
+  int grid_x_f, grid_x_b;
+};
+
+// Fills nchunk_* of every block and the launch plan; returns 0 or a negative stg_status
+// (message in err).  Pure host arithmetic.
+int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen);
+
+// Launchers (enqueue only).
+int launch_xmoments(const float* x, int B, int T, int N, int C, double* xmom, cudaStream_t s);
+int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
+int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
+
+}  // namespace stg

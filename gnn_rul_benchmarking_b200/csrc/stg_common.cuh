@@ -1,0 +1,77 @@
+// Shared device helpers for the sm_100a kernels of the FC_STGNN hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define STG_DEVINL __device__ __forceinline__
+
+namespace stg {
+
+constexpr int kMaxWin = 4;        // largest time_window_size the kernels index (reference uses 2)
+constexpr float kLeaky = 0.01f;   // F.leaky_relu default slope (Model_Base.py:60,107)
+
+STG_DEVINL float lrelu(float v) { return v > 0.f ? v : kLeaky * v; }
+STG_DEVINL float lrelu_grad(float v) { return v > 0.f ? 1.f : kLeaky; }
+
+STG_DEVINL float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+STG_DEVINL float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) ---------------------------
+STG_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+STG_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+STG_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+STG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16.
+STG_DEVINL void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Cooperative staging of `nfl` contiguous floats (4-byte aligned source) into shared memory.
+// Element i lands at dst[shift + i] with shift = ((uintptr_t)src & 15) / 4 so that the 16-byte
+// aligned body can go through one TMA bulk copy; the (<4 float) head and tail use plain loads.
+// Returns shift.  All threads of the CTA must call it; `bar` must be initialised with count 1.
+// The caller waits with mbar_wait(bar, parity) + __syncthreads().
+STG_DEVINL int stage_floats_tma(float* dst16, const float* src, int nfl, uint64_t* bar, int tid) {
+  const int shift = (int)(((uintptr_t)src & 15u) >> 2);
+  int head = shift ? (4 - shift) : 0;
+  if (head > nfl) head = nfl;
+  const int body = ((nfl - head) >> 2) << 2;
+  const int tail = nfl - head - body;
+  if (tid == 0) {
+    mbar_expect_tx(bar, (uint32_t)body * 4u);   // body == 0: plain arrive completes the phase
+    if (body) tma_bulk_g2s(dst16 + shift + head, src + head, (uint32_t)body * 4u, bar);
+  }
+  if (tid < head) dst16[shift + tid] = src[tid];
+  if (tid < tail) dst16[shift + head + body + tid] = src[head + body + tid];
+  return shift;
+}
+
+}  // namespace stg

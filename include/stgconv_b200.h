@@ -1,0 +1,113 @@
+/* stgconv_b200.h -- C ABI of the B200 (sm_100a) spatio-temporal graph-conv hot path.
+ *
+ * Drop-in boundary for the FC_STGNN path of Frank-Wang-oss/GNN_RUL_Benchmarking.  The
+ * reference is pure Python/PyTorch and has no FFI of its own; the "interface each entry
+ * point replaces" is therefore the Python call the reference makes at that place
+ * (file:line relative to the reference tree).  INTEGRATION.md shows the ctypes binding a
+ * maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.
+ *   - all tensors are contiguous float32 unless stated; "dev" pointers are device memory of
+ *     the CUDA device current on the calling thread, "host" pointers are host memory
+ *     (pinned memory makes the copies asynchronous).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device
+ *     entry points only enqueue work; they never synchronise.
+ *   - every function returns STG_OK (0) or a negative stg_status; stg_last_error() gives the
+ *     message of the last failure on the calling thread.  (The reference raises Python
+ *     exceptions; the Python host layer turns a non-zero status into RuntimeError/ValueError.)
+ */
+#ifndef STGCONV_B200_H
+#define STGCONV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum stg_status {
+  STG_OK = 0,
+  STG_ERR_INVALID = -1,      /* bad shape / null pointer / inconsistent sizes   */
+  STG_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels are built for    */
+  STG_ERR_CUDA = -3,         /* a CUDA runtime call failed                      */
+  STG_ERR_WORKSPACE = -4     /* caller-provided workspace too small             */
+} stg_status;
+
+const char* stg_last_error(void);
+/* library / build identification, e.g. "stgconv_b200 0.1 sm_100a". */
+const char* stg_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph-conv block  ==  GraphConvpoolMPNN_block_v6   (models/FC_STGNN/Model_Base.py:175-225)
+ *   x [B,T,N,C] -> out [B,L,N,H],  L = (T-w)/stride + 1, pool_choice = 'mean'
+ *   = Conv_GraphST unfold (:137-148) -> Dot_Graph_Construction_weights (:44-67) -> * Mask_Matrix
+ *     (:150-170,203) -> BatchNorm1d(C) (:183,206-208) -> MPNN_mk_v2 k=1 (:72-107) -> mean over w.
+ * Up to STG_MAX_BLOCKS blocks that read the SAME x (FC_STGNN_RUL uses two: Model.py:26-27,74-75)
+ * run in one launch sequence.
+ * ---------------------------------------------------------------------------------------- */
+#define STG_MAX_BLOCKS 2
+
+typedef struct stg_block_desc {
+  /* hyper-parameters (Model_Base.py:176-188) */
+  int32_t H;          /* output_dim                                  */
+  int32_t w;          /* time_window_size                            */
+  int32_t stride;     /* stride                                      */
+  float decay;        /* Mask_Matrix decay                           */
+  /* parameters, device pointers (state_dict names in comments) */
+  const float* Wm;    /* graph_construction.mapping.weight [C,C]     */
+  const float* bm;    /* graph_construction.mapping.bias   [C]       */
+  const float* bn0_w; /* BN.weight [C]                               */
+  const float* bn0_b; /* BN.bias   [C]                               */
+  float* bn0_rm;      /* BN.running_mean [C]  (updated when training)*/
+  float* bn0_rv;      /* BN.running_var  [C]                         */
+  const float* Wt;    /* MPNN.theta.0.weight [H,C]                   */
+  const float* bt;    /* MPNN.theta.0.bias   [H]                     */
+  const float* bn1_w; /* MPNN.bn1.weight [H]                         */
+  const float* bn1_b; /* MPNN.bn1.bias   [H]                         */
+  float* bn1_rm;      /* MPNN.bn1.running_mean [H]                   */
+  float* bn1_rv;      /* MPNN.bn1.running_var  [H]                   */
+  /* outputs / saved-for-backward, device pointers */
+  float* out;         /* [B, L, N, H] with sample stride out_bstride (floats)              */
+  int64_t out_bstride;/* >= L*N*H; lets two blocks write straight into the FC-head input   */
+  float* yp;          /* training only: pre-BN Y' [B,L,w*N,H] (saved for backward)         */
+  double* stats;      /* training only: STG_BLOCK_STATS_DOUBLES(C,H) doubles of batch stats*/
+} stg_block_desc;
+
+/* layout of stg_block_desc.stats (doubles):
+ *   [0,H)        sum_R  Y'            [H,2H)      sum_R Y'^2          (forward)
+ *   [2H,3H)      sum_R  dYn           [3H,4H)     sum_R dYn*Yhat      (backward)
+ *   [4H,4H+C)    sum_R  dXhat         [4H+C,4H+2C) sum_R dXhat*Xhat   (backward)          */
+#define STG_BLOCK_STATS_DOUBLES(C, H) (4 * (H) + 2 * (C))
+
+/* gradients of one block, device pointers; all are ACCUMULATED into (+=) except dxp. */
+typedef struct stg_block_grads {
+  const float* dout;  /* [B,L,N,H], sample stride dout_bstride                              */
+  int64_t dout_bstride;
+  float* dWm; float* dbm; float* dbn0_w; float* dbn0_b;
+  float* dWt; float* dbt; float* dbn1_w; float* dbn1_b;
+  float* dxp;         /* [B,T,N,C] scratch: this block's dx before the BN-0 mean terms      */
+} stg_block_grads;
+
+/* Per-time-step moments of x for the BatchNorm1d(C) of every block reading x:
+ *   xmom[t*C+c] = sum_{b,n} x[b,t,n,c],  xmom[T*C + t*C+c] = sum x^2     (2*T*C doubles, zeroed here)
+ * (training only; replaces the batch-statistics half of Model_Base.py:206-208). */
+int stg_block_xmoments(const float* x_dev, int B, int T, int N, int C, double* xmom_dev, void* stream);
+
+/* Forward of nblk blocks on the same x.  training=0 uses running statistics (model.eval(),
+ * trainer.py:155) and needs neither xmom nor yp/stats.  training=1 uses batch statistics,
+ * updates running_mean/var with `momentum` (unbiased variance) and fills yp/stats. */
+int stg_block_forward(const float* x_dev, int B, int T, int N, int C, const stg_block_desc* blk, int nblk,
+                      const double* xmom_dev, int training, float momentum, float eps, void* stream);
+
+/* Backward of the same (training mode).  Writes dx [B,T,N,C] (overwritten, summed over the
+ * blocks) and accumulates the parameter gradients. */
+int stg_block_backward(const float* x_dev, int B, int T, int N, int C, const stg_block_desc* blk,
+                       const stg_block_grads* grads, int nblk, const double* xmom_dev, float eps,
+                       float* dx_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STGCONV_B200_H */
