@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- windows/s of one FC_STGNN training step (forward + MSE + backward + Adam, i.e. one
+`Algorithm.update`, algorithms/algorithms.py:67-76) on the BASELINE.json metric config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload S1|S2]
+
+Workload S1 (default) = BASELINE.json configs[1] "FC_STGNN on CMAPSS FD004, batch=256, 1xB200" with the
+reference's own FD004 hyper-parameters (configs/hparams.py:149-151: 14 sensors, 25 patches of 2,
+C=16, H=8); S2 = the north_star synthetic block shape [B=256,T=50,N=21,C=14].  Synthetic U(0,1)
+windows, random-init weights (no dataset ships with the reference).
+
+One JSON line on stdout (rank 0):
+  value     windows/s over all ranks, inputs already resident in HBM
+  e2e       same step through the reference-facing API (FC_STGNN.update) with pinned HOST buffers:
+            H2D of X,y and D2H of the loss inside the timed region
+  roofline  dominant kernel of libstgconv_b200.so, timed with CUDA events on its stream during a
+            second pass over the same steps (stg_profile_*), algorithmic bytes from DESIGN.md
+  cpu_baseline  the CPU oracle port (oracle/fc_stgnn_oracle.py) on this box's host cores, bounded sample
+`--impl reference` times that CPU port alone (all host threads) and prints the same line shape.
+Timing: per-step CUDA-event pairs, L2 flushed (256 MiB memset) between steps outside the pairs,
+barrier + synchronize on both sides of the loop, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "windows/s (fwd+bwd) FC_STGNN CMAPSS-FD004"
+UNIT = "windows/s"
+L2_FLUSH_BYTES = 256 << 20
+
+WORKLOADS = {   # name -> (oracle.CONFIGS key, description)
+    "S1": ("FD004", "FC_STGNN FD004 hparams: X[256,14,50] -> T=25,N=14,C=16,H=8"),
+    "S2": ("S2", "FC_STGNN synthetic north_star shape: X[256,21,50] -> T=50,N=21,C=14,H=7"),
+}
+# configs/hparams.py:133 (FD004 train_params; batch overridden by BASELINE.json to 256)
+HPARAMS = dict(num_epochs=81, batch_size=256, weight_decay=1e-4, learning_rate=1e-3)
+
+
+def model_cfg(name):
+    # kept in sync with oracle.fc_stgnn_oracle.CONFIGS by tests/test_host_logic.py
+    from gnn_rul_benchmarking_b200.configs import CONFIGS
+    return dict(CONFIGS[WORKLOADS[name][0]])
+
+
+def algorithmic_bytes(cfg, B):
+    """fp32 bytes the two fused graph-conv blocks must move per launch."""
+    T, N, h = cfg["num_patch"], cfg["num_node"], cfg["hidden_dim"]
+    C, H = 2 * h, h
+    L = (T - 2) // 1 + 1 + (T - 2) // 2 + 1
+    fwd = 4 * (T * N * C + L * N * H) * B                 # read x, write out1,out2
+    bwd = 4 * (2 * T * N * C + L * N * H) * B             # read x, read dout, write dx
+    return {"fwd": fwd, "bwd": bwd}
+
+
+KERNEL_BYTES_KIND = {"k_block_fwd": "fwd", "k_block_bwd": "bwd"}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as fh:
+                return float(json.load(fh)["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [int(float(r[0])) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [int(float(r[1])) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_steps(cfg, B, steps, warmup, budget_s=None):
+    """The CPU oracle port's update (fwd + MSE + bwd + Adam) on this box's host cores.
+    Returns (ms_per_step, steps_done, threads)."""
+    from oracle import fc_stgnn_oracle as orc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    alg = orc.OracleAlgorithm(cfg, HPARAMS, seed=0)
+    X, y = torch.rand(B, cfg["num_node"], cfg["num_patch"] * cfg["patch_size"]), torch.rand(B, 1)
+    for _ in range(warmup):
+        alg.update(X, y)
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        alg.update(X, y)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return 1e3 * dt / done, done, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = model_cfg(args.workload)
+    B = args.batch
+    ms, done, threads = cpu_reference_steps(cfg, B, args.steps, args.warmup)
+    val = B / (ms / 1e3)
+    sample = f"{done} update steps of B={B} ({args.workload}) on {threads} host threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][1]}", "global_batch": B,
+                   "step": "fwd+mse+bwd+adam", "device": "cpu"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_native(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the native arm has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gnn_rul_benchmarking_b200 import _lib
+    from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
+    from gnn_rul_benchmarking_b200.dp import FlatGradAllReduce
+    _lib.load()
+
+    cfg = model_cfg(args.workload)
+    B = args.batch                                   # per-GPU batch (weak scaling)
+    L_in = cfg["num_patch"] * cfg["patch_size"]
+    torch.manual_seed(0)
+    alg = get_algorithm_class("FC_STGNN")(cfg, HPARAMS, dev).to(dev)
+    alg.train()
+    dp = FlatGradAllReduce(alg.model) if world > 1 else None
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    nbuf = 4
+    Xh = [torch.rand(B, cfg["num_node"], L_in, generator=g).pin_memory() for _ in range(nbuf)]
+    yh = [torch.rand(B, 1, generator=g).pin_memory() for _ in range(nbuf)]
+    Xd = [t.to(dev) for t in Xh]
+    yd = [t.to(dev) for t in yh]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        return alg.step(Xd[i % nbuf], yd[i % nbuf])
+
+    def step_e2e(i):
+        X = Xh[i % nbuf].to(dev, non_blocking=True)
+        y = yh[i % nbuf].to(dev, non_blocking=True)
+        return alg.update(X, y, 1)["loss"]
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            flush.zero_()
+            ev[i][0].record()
+            fn(i)
+            ev[i][1].record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for i in range(args.warmup):
+        step_resident(i)
+    for i in range(max(3, args.warmup // 2)):
+        step_e2e(i)
+    with ClockSampler(local) as clk:
+        ms_res = timed(step_resident, args.steps)
+        ms_e2e = timed(step_e2e, args.steps)
+    # second pass: same steps with per-kernel events of our library (roofline of the dominant kernel)
+    with _lib.kernel_profile() as prof:
+        timed(step_resident, args.steps)
+    kern = prof.result()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = measured_peak_gbs()
+    ab = algorithmic_bytes(cfg, B)
+    roof = None
+    launches = sum(n for _, n in kern.values())
+    cand = {k: v for k, v in kern.items() if k in KERNEL_BYTES_KIND}
+    if cand:
+        name = max(cand, key=lambda k: cand[k][0])
+        tot_ms, n = cand[name]
+        avg_s = tot_ms / n / 1e3
+        nbytes = ab[KERNEL_BYTES_KIND[name]]
+        achieved = nbytes / avg_s / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "peak_source": peak_kind,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "algorithmic_bytes": nbytes,
+                "avg_launch_us": avg_s * 1e6,
+                "share_of_lib_time": tot_ms / max(1e-9, sum(t for t, _ in kern.values())),
+                "kernels_us": {k: round(1e3 * t / n2, 2) for k, (t, n2) in kern.items()}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ms_cpu, done, threads = cpu_reference_steps(cfg, B, 10_000, 2, budget_s=args.cpu_budget)
+        cpu = {"value": B / (ms_cpu / 1e3), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{done} update steps of B={B} ({args.workload}), {ms_cpu:.1f} ms/step, oracle port"}
+    h2d = Xh[0].numel() * 4 + yh[0].numel() * 4
+    line = {
+        "metric": METRIC, "value": world * B / (ms_res / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][1]}", "global_batch": world * B,
+                   "per_gpu_batch": B, "step": "fwd+mse+bwd+adam", "parallelism": f"dp{world}",
+                   "l2": "flushed between steps (256 MiB memset outside the event pairs)"},
+        "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": int(round(launches / args.steps)) * args.steps,
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="S1", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=256, help="windows per GPU per step")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

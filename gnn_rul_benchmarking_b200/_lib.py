@@ -45,6 +45,11 @@ SIGNATURES = {
                                     C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "stg_block_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(StgBlockDesc),
                                      C.POINTER(StgBlockGrads), C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "stg_profile_enable": (C.c_int, [C.c_int]),
+    "stg_profile_reset": (C.c_int, []),
+    "stg_profile_slots": (C.c_int, []),
+    "stg_profile_name": (C.c_char_p, [C.c_int]),
+    "stg_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -84,3 +89,28 @@ def check(status: int, what: str = "") -> None:
     if status in (-1, -2):
         raise ValueError(f"{what}: {msg} (status {status})")
     raise StgError(f"{what}: {msg} (status {status})")
+
+
+class kernel_profile:
+    """Context manager around stg_profile_*: per-kernel CUDA-event durations of the launches made
+    inside the `with` block.  .result() -> {kernel_name: (total_ms, launches)} (synchronises)."""
+
+    def __enter__(self):
+        lib = load()
+        lib.stg_profile_reset()
+        lib.stg_profile_enable(1)
+        return self
+
+    def __exit__(self, *exc):
+        load().stg_profile_enable(0)
+        return False
+
+    def result(self):
+        lib = load()
+        out = {}
+        for slot in range(lib.stg_profile_slots()):
+            ms, n = C.c_double(0.0), C.c_int64(0)
+            check(lib.stg_profile_read(slot, C.byref(ms), C.byref(n)), "stg_profile_read")
+            if n.value:
+                out[lib.stg_profile_name(slot).decode()] = (ms.value, n.value)
+        return out

@@ -916,7 +916,10 @@ int launch_xmoments(const float* x, int B, int T, int N, int C, double* xmom, cu
   cudaMemsetAsync(xmom, 0, sizeof(double) * 2 * T * C, s);
   int nb = (B + 15) / 16;
   if (nb > 64) nb = 64;
-  k_xmoments<<<dim3(T, nb), 256, 2 * C * sizeof(float), s>>>(x, B, T, N, C, xmom);
+  {
+    ProfScope ps(kProfXmoments, s);
+    k_xmoments<<<dim3(T, nb), 256, 2 * C * sizeof(float), s>>>(x, B, T, N, C, xmom);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -930,14 +933,19 @@ int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   if (a.training) {
     for (int z = 0; z < a.nblk; ++z)
       cudaMemsetAsync(a.b[z].stats, 0, sizeof(double) * (4 * a.b[z].H + 2 * a.C), s);
-    v->fwd_train<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max, p.wpc_f, slot);
+    {
+      ProfScope ps(kProfFwdMain, s);
+      v->fwd_train<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max, p.wpc_f, slot);
+    }
     long long tot = 0;
     for (int z = 0; z < a.nblk; ++z) {
       const long long t = (long long)a.B * a.b[z].L * a.N * a.b[z].H;
       tot = t > tot ? t : tot;
     }
+    ProfScope ps(kProfFwdFin, s);
     k_block_fwd_fin<<<dim3((unsigned)((tot + 255) / 256), 1, a.nblk), 256, 0, s>>>(a);
   } else {
+    ProfScope ps(kProfFwdMain, s);
     v->fwd_eval<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max, p.wpc_f, slot);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
@@ -958,9 +966,16 @@ int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   }
   int g = (int)((rows + 255) / 256);
   if (g > 592) g = 592;
-  v->bwd_stats<<<dim3(g, 1, a.nblk), 256, 0, s>>>(a);
-  v->bwd<<<dim3(p.grid_x_b, a.B, a.nblk), p.threads_b, p.smem_b, s>>>(a, rows_max, p.wpc_b, slot);
+  {
+    ProfScope ps(kProfBwdStats, s);
+    v->bwd_stats<<<dim3(g, 1, a.nblk), 256, 0, s>>>(a);
+  }
+  {
+    ProfScope ps(kProfBwdMain, s);
+    v->bwd<<<dim3(p.grid_x_b, a.B, a.nblk), p.threads_b, p.smem_b, s>>>(a, rows_max, p.wpc_b, slot);
+  }
   const long long tot = (long long)a.B * a.T * a.N * a.C;
+  ProfScope ps(kProfBwdFin, s);
   k_block_bwd_fin<<<(unsigned)((tot + 255) / 256), 256, a.nblk * (4 * a.C + a.T) * sizeof(float), s>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

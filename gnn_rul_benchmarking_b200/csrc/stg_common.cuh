@@ -74,4 +74,17 @@ STG_DEVINL int stage_floats_tma(float* dst16, const float* src, int nfl, uint64_
   return shift;
 }
 
+// ---- per-kernel CUDA-event timing (stg_profile_* in the C ABI; off by default) ---------------
+enum ProfSlot {
+  kProfXmoments = 0, kProfFwdMain, kProfFwdFin, kProfBwdStats, kProfBwdMain, kProfBwdFin, kProfSlots
+};
+// Records an event pair around the launches issued while the scope is alive (host-side no-op when
+// profiling is disabled).  Events go on the same stream as the kernels.
+struct ProfScope {
+  int idx;
+  cudaStream_t s;
+  ProfScope(int slot, cudaStream_t stream);
+  ~ProfScope();
+};
+
 }  // namespace stg

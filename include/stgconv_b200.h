@@ -107,6 +107,19 @@ int stg_block_backward(const float* x_dev, int B, int T, int N, int C, const stg
                        const stg_block_grads* grads, int nblk, const double* xmom_dev, float eps,
                        float* dx_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Per-kernel timing (measurement aid, no reference counterpart: the reference has no profiler,
+ * SURVEY.md section 5).  When enabled, every kernel launch of this library is bracketed by a
+ * cudaEvent pair on the launching stream; stg_profile_read() synchronises on the recorded events
+ * of one kernel slot and returns their summed duration and the number of launches since the
+ * last stg_profile_reset().
+ * ---------------------------------------------------------------------------------------- */
+int stg_profile_enable(int on);
+int stg_profile_reset(void);
+int stg_profile_slots(void);
+const char* stg_profile_name(int slot);
+int stg_profile_read(int slot, double* total_ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif
