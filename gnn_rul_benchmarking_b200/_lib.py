@@ -36,6 +36,50 @@ class StgBlockGrads(C.Structure):
     ]
 
 
+MAX_BLOCKS = 2      # STG_MAX_BLOCKS
+
+
+class StgModelDims(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("T", C.c_int32), ("P", C.c_int32), ("K", C.c_int32),
+                ("EH", C.c_int32), ("E", C.c_int32), ("H", C.c_int32),
+                ("w", C.c_int32 * MAX_BLOCKS), ("stride", C.c_int32 * MAX_BLOCKS),
+                ("decay", C.c_float), ("pe_dropout", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float)]
+
+
+class StgBN(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p)]
+
+
+class StgModelBlock(C.Structure):
+    _fields_ = [("Wm", C.c_void_p), ("bm", C.c_void_p), ("bn0", StgBN), ("Wt", C.c_void_p), ("bt", C.c_void_p),
+                ("bn1", StgBN)]
+
+
+class StgModelParams(C.Structure):
+    _fields_ = [("conv1_w", C.c_void_p), ("bn1", StgBN), ("conv2_w", C.c_void_p), ("bn2", StgBN),
+                ("lin_w", C.c_void_p), ("lin_b", C.c_void_p), ("bn3", StgBN), ("pe", C.c_void_p),
+                ("blk", StgModelBlock * MAX_BLOCKS), ("fc_w", C.c_void_p * 4), ("fc_b", C.c_void_p * 4)]
+
+
+class StgDropout(C.Structure):
+    _fields_ = [("keep", C.c_void_p), ("seed", C.c_uint64)]
+
+
+MODEL_SIGNATURES = {
+    "stg_model_workspace_bytes": (C.c_size_t, [C.POINTER(StgModelDims)]),
+    "stg_model_forward": (C.c_int, [C.POINTER(StgModelDims), C.POINTER(StgModelParams), C.c_void_p, C.c_void_p,
+                                    C.c_size_t, C.c_int, C.POINTER(StgDropout), C.c_void_p, C.c_void_p]),
+    "stg_model_backward": (C.c_int, [C.POINTER(StgModelDims), C.POINTER(StgModelParams), C.POINTER(StgModelParams),
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(StgDropout), C.c_void_p,
+                                     C.c_void_p]),
+    "stg_model_loss_backward": (C.c_int, [C.POINTER(StgModelDims), C.POINTER(StgModelParams),
+                                          C.POINTER(StgModelParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.POINTER(StgDropout), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "stg_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
+                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+}
+
 # name -> (restype, argtypes); every symbol include/stgconv_b200.h declares
 SIGNATURES = {
     "stg_last_error": (C.c_char_p, []),
@@ -51,6 +95,7 @@ SIGNATURES = {
     "stg_profile_name": (C.c_char_p, [C.c_int]),
     "stg_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
+SIGNATURES.update(MODEL_SIGNATURES)
 
 _lib = None
 

@@ -9,6 +9,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .engine import StgAdam
 from .fc_stgnn import FC_STGNN_RUL
 
 
@@ -38,16 +39,30 @@ class FC_STGNN(Algorithm):
     def __init__(self, configs, hparams, device):
         super().__init__(configs)
         self.model = FC_STGNN_RUL(**configs)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
-                                          weight_decay=hparams["weight_decay"])
+        # same update rule as torch.optim.Adam(lr, weight_decay) (algorithms.py:60-64), one kernel
+        self.optimizer = StgAdam(self.model.engine, lr=hparams["learning_rate"],
+                                 weight_decay=hparams["weight_decay"])
         self.hparams = hparams
+        self._dp_group, self._dp_world = None, 1
+
+    def attach_data_parallel(self, group=None, broadcast=True):
+        """Shard windows across ranks, all-reduce ONE flat gradient buffer per step."""
+        import torch.distributed as dist
+        self._dp_group, self._dp_world = group, dist.get_world_size(group)
+        if broadcast:
+            with torch.no_grad():
+                for t in list(self.model.parameters()) + list(self.model.buffers()):
+                    dist.broadcast(t, 0, group=group)
+        self.optimizer.grad_scale = 1.0 / self._dp_world
 
     def step(self, X, y):
-        """One optimisation step with everything left on the device; returns the loss tensor."""
-        predicted_RUL = self.model(X)
-        loss = self.mse(predicted_RUL, y)
-        self.optimizer.zero_grad()
-        loss.backward()
+        """One optimisation step (forward -> MSE -> backward -> [all-reduce] -> Adam) with everything
+        left on the device; returns the loss as a 0-dim device tensor."""
+        eng = self.model.engine
+        loss = eng.loss_backward(X, y, zero_grad=True)
+        if self._dp_world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(eng.flat["grad"], op=dist.ReduceOp.SUM, group=self._dp_group)
         self.optimizer.step()
         return loss
 

@@ -76,10 +76,15 @@ STG_DEVINL int stage_floats_tma(float* dst16, const float* src, int nfl, uint64_
 
 // ---- per-kernel CUDA-event timing (stg_profile_* in the C ABI; off by default) ---------------
 enum ProfSlot {
-  kProfXmoments = 0, kProfFwdMain, kProfFwdFin, kProfBwdStats, kProfBwdMain, kProfBwdFin, kProfSlots
+  kProfXmoments = 0, kProfFwdMain, kProfFwdFin, kProfBwdStats, kProfBwdMain, kProfBwdFin,
+  kProfEncF1, kProfEncF2, kProfEncF3, kProfEncF4, kProfEncB1, kProfEncB2, kProfEncB3, kProfEncB4,
+  kProfHeadFc1, kProfHeadTail, kProfHeadBwd1, kProfAdam, kProfZero, kProfSlots
 };
 // Records an event pair around the launches issued while the scope is alive (host-side no-op when
 // profiling is disabled).  Events go on the same stream as the kernels.
+int set_err(int code, const char* fmt, ...);   // thread-local message for stg_last_error()
+int check_cuda(const char* what);
+
 struct ProfScope {
   int idx;
   cudaStream_t s;

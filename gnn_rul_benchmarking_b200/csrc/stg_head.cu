@@ -1,0 +1,343 @@
+// FC head of FC_STGNN_RUL (Model.py:30-39,83: Linear(F->J)+ReLU, Linear(J->J)+ReLU, Linear(J->H)+ReLU,
+// Linear(H->1)), nn.MSELoss (algorithms.py:44,70) and torch.optim.Adam (algorithms.py:60-64), sm_100a.
+//
+//   k_head_fc1   z1[b][j] = b1[j] + sum_k feat[b][k] W1[j][k]       skinny GEMM, one CTA per SPB samples
+//   k_head_tail  per-sample tail (fc2..fc4), optional MSE + backward of the tail -> d1, dW2..dW4, db*
+//   k_head_bwd1  dfeat[b][k] = sum_j d1[b][j] W1[j][k];  dW1[j][k] += sum_b d1[b][j] feat[b][k]
+//   k_adam       flat multi-tensor Adam with L2 weight decay folded into the gradient
+#include <math.h>
+
+#include "stg_model.cuh"
+
+namespace stg {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+template <int JP, int SPB>
+__global__ void __launch_bounds__(256) k_head_fc1(const HeadArgs a) {
+  __shared__ float red[8][SPB * JP];
+  const int b0 = blockIdx.x * SPB, tid = threadIdx.x, J = a.J, F = a.F;
+  float acc[SPB][JP];
+#pragma unroll
+  for (int s = 0; s < SPB; ++s)
+#pragma unroll
+    for (int j = 0; j < JP; ++j) acc[s][j] = 0.f;
+  for (int k = tid; k < F; k += 256) {
+    float f[SPB];
+#pragma unroll
+    for (int s = 0; s < SPB; ++s) f[s] = (b0 + s < a.B) ? a.feat[(size_t)(b0 + s) * F + k] : 0.f;
+#pragma unroll
+    for (int j = 0; j < JP; ++j)
+      if (j < J) {
+        const float w = a.W1[(size_t)j * F + k];
+#pragma unroll
+        for (int s = 0; s < SPB; ++s) acc[s][j] = fmaf(f[s], w, acc[s][j]);
+      }
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int s = 0; s < SPB; ++s)
+#pragma unroll
+    for (int j = 0; j < JP; ++j) {
+      const float v = warp_sum(acc[s][j]);
+      if (lane == 0) red[warp][s * JP + j] = v;
+    }
+  __syncthreads();
+  if (tid < SPB * JP) {
+    const int s = tid / JP, j = tid - s * JP;
+    if (j < J && b0 + s < a.B) {
+      float v = a.b1[j];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][tid];
+      a.z1[(size_t)(b0 + s) * J + j] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MODE 0: forward only (pred).  MODE 1: backward with given dpred.  MODE 2: fused MSE + backward.
+template <int MODE>
+__global__ void __launch_bounds__(128) k_head_tail(const HeadArgs a, int TB) {
+  extern __shared__ __align__(16) float sm[];
+  const int J = a.J, H = a.H, tid = threadIdx.x, nt = blockDim.x;
+  const int TBP = TB + 1;
+  float* W2 = sm;                 // [J][J]
+  float* W3 = W2 + J * J;         // [H][J]
+  float* W4 = W3 + H * J;         // [H]
+  float* bb = W4 + H;             // b2[J] b3[H] b4[1]
+  float* acc = bb + J + H + 1;    // dW2[J*J] db2[J] dW3[H*J] db3[H] dW4[H] db4[1] db1[J] loss[1]
+  const int nacc = J * J + J + H * J + H + H + 1 + J + 1;
+  float* a1 = acc + nacc;         // [J][TBP]   relu(z1)  (<=0 stored as 0; mask == a1 > 0)
+  float* a2 = a1 + J * TBP;       // [J][TBP]
+  float* a3 = a2 + J * TBP;       // [H][TBP]
+  float* dd2 = a3 + H * TBP;      // [J][TBP]   gradient wrt z2
+  float* dd3 = dd2 + J * TBP;     // [H][TBP]   gradient wrt z3
+  float* dd1 = dd3 + H * TBP;     // [J][TBP]   gradient wrt z1
+  float* dps = dd1 + J * TBP;     // [TBP]      dpred
+  for (int i = tid; i < J * J; i += nt) W2[i] = a.W2[i];
+  for (int i = tid; i < H * J; i += nt) W3[i] = a.W3[i];
+  for (int i = tid; i < H; i += nt) W4[i] = a.W4[i];
+  for (int i = tid; i < J; i += nt) bb[i] = a.b2[i];
+  for (int i = tid; i < H; i += nt) bb[J + i] = a.b3[i];
+  if (tid == 0) bb[J + H] = a.b4[0];
+  if (MODE) for (int i = tid; i < nacc; i += nt) acc[i] = 0.f;
+  __syncthreads();
+  const int b = blockIdx.x * TB + tid;
+  const bool act = tid < TB && b < a.B;
+  float pred = 0.f;
+  if (act) {
+    for (int j = 0; j < J; ++j) a1[j * TBP + tid] = fmaxf(a.z1[(size_t)b * J + j], 0.f);
+    for (int i = 0; i < J; ++i) {
+      float v = bb[i];
+      for (int j = 0; j < J; ++j) v = fmaf(W2[i * J + j], a1[j * TBP + tid], v);
+      a2[i * TBP + tid] = fmaxf(v, 0.f);
+    }
+    for (int i = 0; i < H; ++i) {
+      float v = bb[J + i];
+      for (int j = 0; j < J; ++j) v = fmaf(W3[i * J + j], a2[j * TBP + tid], v);
+      a3[i * TBP + tid] = fmaxf(v, 0.f);
+    }
+    pred = bb[J + H];
+    for (int i = 0; i < H; ++i) pred = fmaf(W4[i], a3[i * TBP + tid], pred);
+    if (a.pred) a.pred[b] = pred;
+  }
+  if (MODE == 0) return;
+  float dp = 0.f, lossv = 0.f;
+  if (act) {
+    if (MODE == 2) {
+      const float e = pred - a.y[b];
+      lossv = e * e / (float)a.B;
+      dp = 2.f * e / (float)a.B;
+    } else {
+      dp = a.dpred[b];
+    }
+    for (int i = 0; i < H; ++i) dd3[i * TBP + tid] = a3[i * TBP + tid] > 0.f ? dp * W4[i] : 0.f;
+    for (int j = 0; j < J; ++j) {
+      float v = 0.f;
+      if (a2[j * TBP + tid] > 0.f)
+        for (int i = 0; i < H; ++i) v = fmaf(dd3[i * TBP + tid], W3[i * J + j], v);
+      dd2[j * TBP + tid] = v;
+    }
+    for (int j = 0; j < J; ++j) {
+      float v = 0.f;
+      if (a1[j * TBP + tid] > 0.f)
+        for (int i = 0; i < J; ++i) v = fmaf(dd2[i * TBP + tid], W2[i * J + j], v);
+      dd1[j * TBP + tid] = v;
+      a.d1[(size_t)b * J + j] = v;
+    }
+    dps[tid] = dp;
+  }
+  if (MODE == 2) {
+    lossv = warp_sum(lossv);
+    if ((tid & 31) == 0) atomicAdd(&acc[nacc - 1], lossv);
+  }
+  __syncthreads();
+  const int rows = min(TB, a.B - blockIdx.x * TB);
+  // weight gradients: one owner thread per entry, loop over the CTA's samples
+  float* gW2 = acc; float* gb2 = gW2 + J * J; float* gW3 = gb2 + J; float* gb3 = gW3 + H * J;
+  float* gW4 = gb3 + H; float* gb4 = gW4 + H; float* gb1 = gb4 + 1;
+  for (int e = tid; e < nacc - 1; e += nt) {
+    float v = 0.f;
+    if (e < J * J) {
+      const int i = e / J, j = e - i * J;
+      for (int r = 0; r < rows; ++r) v = fmaf(dd2[i * TBP + r], a1[j * TBP + r], v);
+    } else if (e < J * J + J) {
+      const int i = e - J * J;
+      for (int r = 0; r < rows; ++r) v += dd2[i * TBP + r];
+    } else if (e < J * J + J + H * J) {
+      const int q = e - (J * J + J), i = q / J, j = q - i * J;
+      for (int r = 0; r < rows; ++r) v = fmaf(dd3[i * TBP + r], a2[j * TBP + r], v);
+    } else if (e < J * J + J + H * J + H) {
+      const int i = e - (J * J + J + H * J);
+      for (int r = 0; r < rows; ++r) v += dd3[i * TBP + r];
+    } else if (e < J * J + J + H * J + 2 * H) {
+      const int i = e - (J * J + J + H * J + H);
+      for (int r = 0; r < rows; ++r) v = fmaf(dps[r], a3[i * TBP + r], v);
+    } else if (e == J * J + J + H * J + 2 * H) {
+      for (int r = 0; r < rows; ++r) v += dps[r];
+    } else {
+      const int j = e - (J * J + J + H * J + 2 * H + 1);
+      for (int r = 0; r < rows; ++r) v += dd1[j * TBP + r];
+    }
+    acc[e] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < J * J; i += nt) atomicAdd(&a.dW2[i], gW2[i]);
+  for (int i = tid; i < J; i += nt) { atomicAdd(&a.db2[i], gb2[i]); atomicAdd(&a.db1[i], gb1[i]); }
+  for (int i = tid; i < H * J; i += nt) atomicAdd(&a.dW3[i], gW3[i]);
+  for (int i = tid; i < H; i += nt) { atomicAdd(&a.db3[i], gb3[i]); atomicAdd(&a.dW4[i], gW4[i]); }
+  if (tid == 0) {
+    atomicAdd(&a.db4[0], gb4[0]);
+    if (MODE == 2 && a.loss) atomicAdd(a.loss, acc[nacc - 1]);
+  }
+}
+
+static size_t tail_smem(int J, int H, int TB) {
+  const int TBP = TB + 1;
+  const size_t nacc = (size_t)J * J + J + (size_t)H * J + H + H + 1 + J + 1;
+  return 4 * ((size_t)J * J + (size_t)H * J + H + J + H + 1 + nacc + (size_t)(4 * J + 2 * H + 1) * TBP);
+}
+
+// ------------------------------------------------------------------------------------------
+// grid (ceil(F/128), BS); thread = one feature column k, samples [b_lo, b_hi) of slice blockIdx.y
+template <int JP>
+__global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
+  extern __shared__ __align__(16) float sm[];   // d1 slice [bper][J]
+  const int J = a.J, F = a.F, tid = threadIdx.x;
+  const int b_lo = blockIdx.y * bper, b_hi = min(a.B, b_lo + bper);
+  for (int i = tid; i < (b_hi - b_lo) * J; i += blockDim.x) sm[i] = a.d1[(size_t)b_lo * J + i];
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + tid;
+  if (k >= F) return;
+  float wc[JP], gw[JP];
+#pragma unroll
+  for (int j = 0; j < JP; ++j) {
+    wc[j] = j < J ? a.W1[(size_t)j * F + k] : 0.f;
+    gw[j] = 0.f;
+  }
+  for (int b = b_lo; b < b_hi; ++b) {
+    const float f = a.feat[(size_t)b * F + k];
+    const float* d = sm + (b - b_lo) * J;
+    float df = 0.f;
+#pragma unroll
+    for (int j = 0; j < JP; ++j)
+      if (j < J) {
+        const float dj = d[j];
+        df = fmaf(dj, wc[j], df);
+        gw[j] = fmaf(dj, f, gw[j]);
+      }
+    a.dfeat[(size_t)b * F + k] = df;
+  }
+#pragma unroll
+  for (int j = 0; j < JP; ++j)
+    if (j < J) atomicAdd(&a.dW1[(size_t)j * F + k], gw[j]);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, long long n, const long long* __restrict__ step,
+                                              float lr, float b1, float b2, float eps, float wd, float gscale) {
+  const double t = (double)(*step);
+  const float bc1 = (float)(1.0 - pow((double)b1, t));
+  const float bc2s = (float)sqrt(1.0 - pow((double)b2, t));
+  const float step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    const float gv = fmaf(wd, pv, g[i] * gscale);
+    const float mv = fmaf(1.f - b1, gv - m[i], m[i]);            // torch: lerp(m, g, 1-b1)
+    const float vv = fmaf(1.f - b2, gv * gv, b2 * v[i]);
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2s + eps;
+    p[i] = pv - step_size * (mv / denom);
+  }
+}
+
+struct TickArgs { long long* p[16]; int n; };
+__global__ void k_tick(const TickArgs t) {
+  if (threadIdx.x < t.n && t.p[threadIdx.x]) *t.p[threadIdx.x] += 1;
+}
+
+__global__ void __launch_bounds__(256) k_zero(float4* p, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <int JP, int SPB>
+void fc1_launch(const HeadArgs& a, cudaStream_t s) {
+  k_head_fc1<JP, SPB><<<(a.B + SPB - 1) / SPB, 256, 0, s>>>(a);
+}
+template <int JP>
+void bwd1_launch(const HeadArgs& a, cudaStream_t s) {
+  const int gx = (a.F + 127) / 128;
+  int slices = (2 * 148 + gx - 1) / gx;
+  if (slices > a.B) slices = a.B;
+  int bper = (a.B + slices - 1) / slices;
+  if ((size_t)bper * a.J * 4 > 40 * 1024) bper = (int)(40 * 1024 / (a.J * 4));
+  slices = (a.B + bper - 1) / bper;
+  k_head_bwd1<JP><<<dim3(gx, slices), 128, (size_t)bper * a.J * 4, s>>>(a, bper);
+}
+
+int tail_tb(int J) { return J <= 32 ? 128 : 32; }
+bool g_tail_attr[64] = {};
+void tail_attrs() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (g_tail_attr[dev]) return;
+  cudaFuncSetAttribute(k_head_tail<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_head_tail<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_head_tail<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  g_tail_attr[dev] = true;
+}
+
+}  // namespace
+
+int launch_head_forward(const HeadArgs& a, cudaStream_t s) {
+  if (a.J > 64 || a.H > 64) return -2;
+  {
+    ProfScope ps(kProfHeadFc1, s);
+    if (a.J <= 16) fc1_launch<16, 4>(a, s);
+    else if (a.J <= 32) fc1_launch<32, 2>(a, s);
+    else if (a.J <= 48) fc1_launch<48, 1>(a, s);
+    else fc1_launch<64, 1>(a, s);
+  }
+  if (a.pred && !a.y && !a.dpred) {      // plain forward: finish the tail now
+    tail_attrs();
+    const int TB = tail_tb(a.J);
+    ProfScope ps(kProfHeadTail, s);
+    k_head_tail<0><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+int launch_head_backward(const HeadArgs& a, cudaStream_t s) {
+  if (a.J > 64 || a.H > 64) return -2;
+  tail_attrs();
+  const int TB = tail_tb(a.J);
+  {
+    ProfScope ps(kProfHeadTail, s);
+    if (a.y) k_head_tail<2><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
+    else k_head_tail<1><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
+  }
+  ProfScope ps(kProfHeadBwd1, s);
+  if (a.J <= 16) bwd1_launch<16>(a, s);
+  else if (a.J <= 32) bwd1_launch<32>(a, s);
+  else if (a.J <= 48) bwd1_launch<48>(a, s);
+  else bwd1_launch<64>(a, s);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+int launch_zero(void* p, size_t bytes, cudaStream_t s) {
+  // bytes must be a multiple of 16 and p 16-byte aligned (workspace segments are)
+  const size_t n4 = bytes / 16;
+  if (!n4) return 0;
+  int grid = (int)((n4 + 255) / 256);
+  if (grid > 1184) grid = 1184;
+  ProfScope ps(kProfZero, s);
+  k_zero<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(p), n4);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, long long* step, float lr, float b1,
+                float b2, float eps, float wd, float gscale, cudaStream_t s) {
+  TickArgs t = {};
+  t.p[0] = step;
+  t.n = 1;
+  k_tick<<<1, 32, 0, s>>>(t);
+  int grid = (int)((n + 255) / 256);
+  if (grid > 1184) grid = 1184;
+  ProfScope ps(kProfAdam, s);
+  k_adam<<<grid, 256, 0, s>>>(p, g, m, v, n, step, lr, b1, b2, eps, wd, gscale);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+int launch_tick(long long* const* counters, int n, cudaStream_t s) {
+  TickArgs t = {};
+  t.n = n > 16 ? 16 : n;
+  for (int i = 0; i < t.n; ++i) t.p[i] = counters[i];
+  k_tick<<<1, 32, 0, s>>>(t);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+}  // namespace stg

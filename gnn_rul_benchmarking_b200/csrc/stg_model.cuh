@@ -1,0 +1,62 @@
+// Kernel-side argument structs of the whole-model engine (encoder, head, Adam) shared between
+// stg_encoder.cu, stg_head.cu and the C-ABI layer stg_model_capi.cu.
+#pragma once
+#include "stg_common.cuh"
+
+namespace stg {
+
+// ---- patch encoder + positional encoding (Model_Base.py:12-41,111-134; Model.py:18-22,45-68) ----
+struct EncArgs {
+  // dims
+  int B, N, T, P, K, EH, E, C;
+  int L1, L2, EL2, pad1;      // conv output lengths, E*L2, conv1 padding (K/2)
+  int R;                      // rows = B*T*N
+  int TR;                     // rows per CTA tile (<= 256)
+  // tensors
+  const float* X;             // [B, N, T*P]
+  const float *W1, *W2, *W3, *b3;
+  const float *g1, *be1, *g2, *be2, *g3, *be3;
+  float *rm1, *rv1, *rm2, *rv2, *rm3, *rv3;
+  const float* pe;            // [>=T, C]
+  const float* keep;          // optional [B*N, T, C] 0/1 mask
+  unsigned long long seed;
+  float pdrop;
+  int training;
+  float momentum, eps;
+  double* st;                 // stats scratch, see enc_stat_off()
+  float* h;                   // [R, C] output of the forward
+  const float* dh;            // [R, C] gradient wrt h
+  float *dW1, *dW2, *dW3, *db3, *dg1, *dbe1, *dg2, *dbe2, *dg3, *dbe3;
+};
+// stats scratch layout (doubles): forward  [S1: 2*EH][S2: 2*E][S3: 2*C]
+//                                 backward [B3: 2*C][B2: 2*E][B1: 2*EH]
+inline __host__ __device__ int enc_stats_doubles(int EH, int E, int C) { return 4 * (EH + E + C); }
+
+int plan_encoder(EncArgs& a, size_t* smem_fwd, size_t* smem_bwd, char* err, size_t errlen);
+int launch_encoder_forward(const EncArgs& a, size_t smem, cudaStream_t s);
+int launch_encoder_backward(const EncArgs& a, size_t smem, cudaStream_t s);
+
+// ---- FC head (Model.py:30-39,83) + MSE -------------------------------------------------------
+struct HeadArgs {
+  int B, F, J, H;             // J = 2H
+  const float* feat;          // [B, F]
+  const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4;
+  float* z1;                  // [B, J] pre-activation of fc1 (workspace)
+  float* d1;                  // [B, J] gradient wrt z1 (workspace)
+  float* pred;                // [B]
+  const float* y;             // [B] targets (fused loss) or nullptr
+  const float* dpred;         // [B] upstream gradient (autograd path) or nullptr
+  float* loss;                // [1] accumulated mean squared error (fused loss)
+  float* dfeat;               // [B, F]
+  float *dW1, *db1, *dW2, *db2, *dW3, *db3, *dW4, *db4;
+};
+int launch_head_forward(const HeadArgs& a, cudaStream_t s);               // feat -> z1 -> pred
+int launch_head_backward(const HeadArgs& a, cudaStream_t s);              // (y | dpred) -> grads, dfeat
+
+// ---- misc -------------------------------------------------------------------------------------
+int launch_zero(void* p, size_t bytes, cudaStream_t s);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, long long* step, float lr, float b1,
+                float b2, float eps, float wd, float gscale, cudaStream_t s);
+int launch_tick(long long* const* counters, int n, cudaStream_t s);
+
+}  // namespace stg

@@ -18,6 +18,7 @@ from collections import OrderedDict
 import torch
 import torch.nn as nn
 
+from . import engine as ENG
 from . import functional as SF
 
 DECAY = 0.7            # Model.py:12
@@ -108,6 +109,7 @@ class GraphConvpoolMPNN_block_v6(nn.Module):
         super().__init__()
         if pool_choice != "mean":
             raise NotImplementedError("FC_STGNN_RUL hard-wires pool_choice='mean' (Model.py:11)")
+        self.num_sensors = num_sensors
         self.time_window_size = time_window_size
         self.stride = stride
         self.output_dim = output_dim
@@ -166,7 +168,22 @@ class FC_STGNN_RUL(nn.Module):
         A = self.positional_encoding(torch.reshape(A, [bs * num_node, tlen, -1]))
         return torch.reshape(A, [bs, num_node, tlen, -1]).transpose(1, 2).contiguous()
 
+    @property
+    def engine(self) -> "ENG.ModelEngine":
+        eng = self.__dict__.get("_engine")
+        if eng is None:
+            eng = ENG.ModelEngine(self)
+            self.__dict__["_engine"] = eng
+        return eng
+
     def forward(self, X):
+        """Whole model in the sm_100a engine (csrc/stg_encoder.cu, stg_block.cu, stg_head.cu): one
+        autograd node; BatchNorm running statistics and num_batches_tracked are updated on the
+        device in training mode."""
+        return ENG.model_forward(self.engine, X)
+
+    def forward_torch_encoder(self, X):
+        """Earlier composition kept for cross-checks: torch encoder/head around the native blocks."""
         h = self.encode(X)
         # MPNN1 and MPNN2 read the same tensor (Model.py:74-75): one fused launch sequence that
         # writes straight into the concatenated feature layout of Model.py:78-81.

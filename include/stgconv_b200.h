@@ -108,6 +108,100 @@ int stg_block_backward(const float* x_dev, int B, int T, int N, int C, const stg
                        float* dx_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Whole model  ==  FC_STGNN_RUL  (models/FC_STGNN/Model.py:5-85) and one optimisation step of
+ * class FC_STGNN (algorithms/algorithms.py:51-76).
+ *
+ *   X [B, N, T*P]  --reshape/transpose (Model.py:45-49)-->  rows (b,t,n) of P samples
+ *     -> Feature_extractor_1DCNN_RUL (Model_Base.py:12-41): Conv1d(1->EH,K,pad K/2,no bias)+BN+ReLU,
+ *        Conv1d(EH->E,K,pad 1,no bias)+BN+ReLU                     -> [rows, E, L2]
+ *     -> nonlin_map2 (Model.py:18-22): Linear(E*L2 -> C=2H) + BatchNorm1d(C)
+ *     -> PositionalEncoding (Model_Base.py:111-134): + pe[t], Dropout(p)      -> h [B,T,N,C]
+ *     -> MPNN1 (w=2,stride 1), MPNN2 (w=2,stride 2) on the same h (Model.py:74-75)
+ *     -> cat(flatten) (Model.py:78-81)                                        -> feat [B,F]
+ *     -> fc: Linear(F->C)+ReLU, Linear(C->C)+ReLU, Linear(C->H)+ReLU, Linear(H->1)  (Model.py:30-39)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct stg_model_dims {
+  int32_t B;      /* windows in this batch                                   */
+  int32_t N;      /* num_node                                                */
+  int32_t T;      /* num_patch                                               */
+  int32_t P;      /* patch_size                                              */
+  int32_t K;      /* encoder_conv_kernel                                     */
+  int32_t EH;     /* encoder_hidden_dim                                      */
+  int32_t E;      /* encoder_out_dim                                         */
+  int32_t H;      /* hidden_dim  (C = 2*H)                                   */
+  int32_t w[STG_MAX_BLOCKS];       /* moving_window  (Model.py:13)           */
+  int32_t stride[STG_MAX_BLOCKS];  /* stride         (Model.py:14)           */
+  float decay;        /* Model.py:12                                         */
+  float pe_dropout;   /* Model.py:24 (0.1)                                   */
+  float bn_momentum;  /* 0.1                                                 */
+  float bn_eps;       /* 1e-5                                                */
+} stg_model_dims;
+
+typedef struct stg_bn {           /* one nn.BatchNorm1d                                   */
+  float* weight; float* bias; float* running_mean; float* running_var;
+  int64_t* num_batches_tracked;   /* incremented by training forwards (may be NULL)       */
+} stg_bn;
+
+typedef struct stg_model_block {  /* one GraphConvpoolMPNN_block_v6 (MPNN1 / MPNN2)         */
+  float* Wm; float* bm;   /* MPNNk.graph_construction.mapping.{weight [C,C],bias [C]} */
+  stg_bn bn0;             /* MPNNk.BN.*             [C]                               */
+  float* Wt; float* bt;   /* MPNNk.MPNN.theta.0.{weight [H,C],bias [H]}               */
+  stg_bn bn1;             /* MPNNk.MPNN.bn1.*       [H]                               */
+} stg_model_block;
+
+typedef struct stg_model_params { /* device pointers, state_dict names in comments        */
+  float* conv1_w;  /* nonlin_map.conv_block1.0.weight [EH,1,K]    */
+  stg_bn bn1;      /* nonlin_map.conv_block1.1.*      [EH]        */
+  float* conv2_w;  /* nonlin_map.conv_block2.0.weight [E,EH,K]    */
+  stg_bn bn2;      /* nonlin_map.conv_block2.1.*      [E]         */
+  float* lin_w;    /* nonlin_map2.0.weight            [C, E*L2]   */
+  float* lin_b;    /* nonlin_map2.0.bias              [C]         */
+  stg_bn bn3;      /* nonlin_map2.1.*                 [C]         */
+  const float* pe; /* positional_encoding.pe[0]       [>=T, C]    */
+  stg_model_block blk[STG_MAX_BLOCKS];
+  float* fc_w[4];  /* fc.fc1..fc4.weight  [C,F] [C,C] [H,C] [1,H] */
+  float* fc_b[4];  /* fc.fc1..fc4.bias                            */
+} stg_model_params;
+/* Gradients use the same struct: every weight/bias pointer addresses the gradient buffer of that
+ * parameter (ACCUMULATED into, +=); running_* / num_batches_tracked / pe are ignored. */
+
+/* Dropout of the positional encoding in training mode:
+ *   keep != NULL : 0/1 float mask laid out like the reference's dropout input [B*N, T, C]
+ *                  (Model.py:64-65) -- used to pin the mask in parity tests;
+ *   keep == NULL : counter-based generator keyed by (seed, element index); the same (seed) must be
+ *                  passed to the backward call.  pe_dropout == 0 disables it. */
+typedef struct stg_dropout { const float* keep; uint64_t seed; } stg_dropout;
+
+/* Bytes of caller-provided device workspace for a batch of dims->B windows (activations saved for
+ * backward + reduction scratch).  0 on invalid dims. */
+size_t stg_model_workspace_bytes(const stg_model_dims* dims);
+
+/* pred[B] = FC_STGNN_RUL.forward(X).  training=1: batch statistics, running stats and
+ * num_batches_tracked updated, activations kept in `workspace` for stg_model_backward. */
+int stg_model_forward(const stg_model_dims* dims, const stg_model_params* params, const float* X_dev,
+                      void* workspace, size_t workspace_bytes, int training, const stg_dropout* drop,
+                      float* pred_dev, void* stream);
+
+/* Gradients of every parameter given dpred[B] = dLoss/dpred, after a training forward on the same
+ * workspace / X / dropout. */
+int stg_model_backward(const stg_model_dims* dims, const stg_model_params* params, const stg_model_params* grads,
+                       const float* X_dev, void* workspace, size_t workspace_bytes, const stg_dropout* drop,
+                       const float* dpred_dev, void* stream);
+
+/* forward -> nn.MSELoss (mean) -> backward in one call (algorithms.py:68-73 without the optimizer):
+ * loss_dev[0] = mean((pred - y)^2), gradients accumulated into `grads`. */
+int stg_model_loss_backward(const stg_model_dims* dims, const stg_model_params* params,
+                            const stg_model_params* grads, const float* X_dev, const float* y_dev,
+                            void* workspace, size_t workspace_bytes, const stg_dropout* drop, float* pred_dev,
+                            float* loss_dev, void* stream);
+
+/* torch.optim.Adam(lr, betas, eps, weight_decay) (algorithms.py:60-64) over ONE flat parameter
+ * buffer: grad += wd*param; m,v EMA; bias correction with step = ++(*step_dev).  n floats. */
+int stg_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n,
+                  int64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Per-kernel timing (measurement aid, no reference counterpart: the reference has no profiler,
  * SURVEY.md section 5).  When enabled, every kernel launch of this library is bracketed by a
  * cudaEvent pair on the launching stream; stg_profile_read() synchronises on the recorded events
