@@ -507,6 +507,7 @@ int plan_encoder(EncArgs& a, size_t* smem_fwd, size_t* smem_bwd, char* err, size
 }
 
 int launch_encoder_forward(const EncArgs& a, size_t smem, cudaStream_t s) {
+  if (a.c2raw && encoder_fast_available(a)) return launch_encoder_fast(a, false, s);
   set_attrs();
   if (a.training)
     for (int ph = 0; ph < 3; ++ph) launch_phase(ph, a, smem, s);
@@ -515,6 +516,7 @@ int launch_encoder_forward(const EncArgs& a, size_t smem, cudaStream_t s) {
 }
 
 int launch_encoder_backward(const EncArgs& a, size_t smem, cudaStream_t s) {
+  if (a.c2raw && encoder_fast_available(a)) return launch_encoder_fast(a, true, s);
   set_attrs();
   for (int ph = 4; ph < 8; ++ph) launch_phase(ph, a, smem, s);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;

@@ -1,0 +1,536 @@
+// Patch encoder, compile-time-dimension fast path (sm_100a).  Same math and phase structure as the
+// generic kernels in stg_encoder.cu (which remain the fallback for every other hyper-parameter set),
+// but: all per-row activations live in registers (loops fully unrolled), and the raw conv2 / linear
+// outputs and the ReLU-masked gradients are kept in the workspace between phases in a
+// [tile][feature][256 rows] layout (perfectly coalesced for one-thread-per-row), so no phase
+// recomputes more than conv1:
+//   F1 conv1 moments | F2 conv1,conv2 -> c2raw, moments | F3 c2raw -> linear -> z3raw, moments | F4 z3raw -> h
+//   B1 dh,z3raw -> BN3 sums | B2 -> dW3,db3, dn2, BN2 sums | B3 -> dW2, dn1, BN1 sums | B4 -> dW1
+#include <math.h>
+
+#include "stg_model.cuh"
+
+namespace stg {
+namespace {
+
+constexpr int kT = 256;          // threads per CTA == rows per tile
+constexpr int kTP = 260;         // smem row pitch of the staged columns (float4-aligned)
+
+template <int P_, int K_, int EH_, int E_, int C_>
+struct EncDims {
+  static constexpr int P = P_, K = K_, EH = EH_, E = E_, C = C_;
+  static constexpr int pad1 = K / 2, L1 = P + 2 * pad1 - K + 1, L2 = L1 + 2 - K + 1;
+  static constexpr int EL2 = E * L2, NL1 = EH * L1;
+};
+
+STG_DEVINL float keep_scale_f(const EncArgs& a, size_t idx) {
+  if (!a.training || a.pdrop <= 0.f) return 1.f;
+  const float sc = 1.f / (1.f - a.pdrop);
+  if (a.keep) return a.keep[idx] * sc;
+  unsigned long long z = a.seed + (unsigned long long)idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.f / 16777216.f);
+  return u >= a.pdrop ? sc : 0.f;
+}
+
+STG_DEVINL void bn_coefs_f(float* dst, int n, const double* stats, double count, const float* g, const float* be,
+                           float* rm, float* rv, float eps, float momentum, bool update) {
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    double m, var;
+    if (stats) {
+      m = stats[c] / count;
+      var = stats[n + c] / count - m * m;
+      if (var < 0.0) var = 0.0;
+      if (update) {
+        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        rm[c] = (1.f - momentum) * rm[c] + momentum * (float)m;
+        rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unb;
+      }
+    } else {
+      m = rm[c];
+      var = rv[c];
+    }
+    const float r = (float)(1.0 / sqrt(var + (double)eps));
+    const float A = g[c] * r;
+    dst[c] = A;
+    dst[n + c] = be[c] - A * (float)m;
+    dst[2 * n + c] = (float)m;
+    dst[3 * n + c] = r;
+  }
+}
+
+STG_DEVINL void stat_add_f(double* sacc, int idx, float v) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[idx], (double)v);
+}
+
+template <class D>
+STG_DEVINL void conv1_row(const float* W1, const float (&x)[D::P], float (&c1)[D::NL1]) {
+#pragma unroll
+  for (int ch = 0; ch < D::EH; ++ch)
+#pragma unroll
+    for (int p = 0; p < D::L1; ++p) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < D::K; ++j) {
+        const int q = p + j - D::pad1;
+        if (q >= 0 && q < D::P) acc = fmaf(W1[ch * D::K + j], x[q], acc);
+      }
+      c1[ch * D::L1 + p] = acc;
+    }
+}
+
+template <class D>
+STG_DEVINL void conv2_row(const float* W2, const float (&a1)[D::NL1], float (&c2)[D::EL2]) {
+#pragma unroll
+  for (int e = 0; e < D::E; ++e) {
+    float acc[D::L2];
+#pragma unroll
+    for (int p = 0; p < D::L2; ++p) acc[p] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < D::EH; ++ch)
+#pragma unroll
+      for (int j = 0; j < D::K; ++j) {
+        const float w = W2[(e * D::EH + ch) * D::K + j];
+#pragma unroll
+        for (int p = 0; p < D::L2; ++p) {
+          const int q = p + j - 1;
+          if (q >= 0 && q < D::L1) acc[p] = fmaf(w, a1[ch * D::L1 + q], acc[p]);
+        }
+      }
+#pragma unroll
+    for (int p = 0; p < D::L2; ++p) c2[e * D::L2 + p] = acc[p];
+  }
+}
+
+// pairs over threads, float4 over the 256 staged rows; f4(pair, r4) returns the partial product sum
+template <int NP, typename Fn>
+STG_DEVINL void pair_reduce_f(float* accW, Fn f) {
+  const int tid = threadIdx.x;
+  if (NP <= kT / 2) {
+    constexpr int slices = NP <= kT / 2 ? kT / (NP > 0 ? NP : 1) : 1;
+    if (tid < NP * slices) {
+      const int pair = tid % NP, sl = tid / NP;
+      float acc = 0.f;
+      for (int r4 = sl; r4 < kT / 4; r4 += slices) acc += f(pair, r4 * 4);
+      atomicAdd(&accW[pair], acc);
+    }
+  } else {
+    for (int pair = tid; pair < NP; pair += kT) {
+      float acc = 0.f;
+      for (int r4 = 0; r4 < kT / 4; ++r4) acc += f(pair, r4 * 4);
+      accW[pair] += acc;
+    }
+  }
+}
+
+STG_DEVINL float dot4(const float4 a, const float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+STG_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <class D, int PH>
+__global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
+  constexpr int P = D::P, K = D::K, EH = D::EH, E = D::E, C = D::C, L1 = D::L1, L2 = D::L2, EL2 = D::EL2, NL1 = D::NL1;
+  constexpr int MAXCH = EH > E ? (EH > C ? EH : C) : (E > C ? E : C);
+  constexpr int NPAIR = PH == 5 ? C * EL2 + C : PH == 6 ? E * EH * K : PH == 7 ? EH * K : 1;
+  __shared__ __align__(16) float W1[EH * K];
+  __shared__ __align__(16) float W2[E * EH * K];
+  __shared__ __align__(16) float W3[C * EL2];
+  __shared__ float b3[C];
+  __shared__ float cf1[4 * EH], cf2[4 * E], cf3[4 * C];
+  __shared__ float q1[2 * EH], q2[2 * E], q3[2 * C];
+  __shared__ double sacc[2 * MAXCH];
+  __shared__ float accW[NPAIR];
+  extern __shared__ __align__(16) float stage[];      // [features][kTP] columns for the pair reductions / pe
+  const int tid = threadIdx.x;
+  const int N = a.N, T = a.T;
+
+  const double cnt1 = (double)a.R * L1, cnt2 = (double)a.R * L2, cnt3 = (double)a.R;
+  const double* S1 = a.st;
+  const double* S2 = S1 + 2 * EH;
+  const double* S3 = S2 + 2 * E;
+  double* Bq3 = a.st + 2 * (EH + E + C);
+  double* Bq2 = Bq3 + 2 * C;
+  double* Bq1 = Bq2 + 2 * E;
+
+  for (int i = tid; i < EH * K; i += kT) W1[i] = a.W1[i];
+  for (int i = tid; i < E * EH * K; i += kT) W2[i] = a.W2[i];
+  for (int i = tid; i < C * EL2; i += kT) W3[i] = a.W3[i];
+  for (int i = tid; i < C; i += kT) b3[i] = a.b3[i];
+  const bool first = blockIdx.x == 0, tr = a.training != 0;
+  if (PH >= 1) bn_coefs_f(cf1, EH, tr ? S1 : nullptr, cnt1, a.g1, a.be1, a.rm1, a.rv1, a.eps, a.momentum, tr && first && PH == 1);
+  if (PH >= 2) bn_coefs_f(cf2, E, tr ? S2 : nullptr, cnt2, a.g2, a.be2, a.rm2, a.rv2, a.eps, a.momentum, tr && first && PH == 2);
+  if (PH >= 3) bn_coefs_f(cf3, C, tr ? S3 : nullptr, cnt3, a.g3, a.be3, a.rm3, a.rv3, a.eps, a.momentum, tr && first && PH == 3);
+  if (PH == 3) for (int i = tid; i < T * C; i += kT) stage[i] = a.pe[i];
+  if (PH >= 5) for (int c = tid; c < C; c += kT) {
+    q3[c] = (float)(Bq3[c] / cnt3);
+    q3[C + c] = (float)(Bq3[C + c] / cnt3);
+    if (PH == 5 && first) { a.dbe3[c] += (float)Bq3[c]; a.dg3[c] += (float)Bq3[C + c]; }
+  }
+  if (PH >= 6) for (int c = tid; c < E; c += kT) {
+    q2[c] = (float)(Bq2[c] / cnt2);
+    q2[E + c] = (float)(Bq2[E + c] / cnt2);
+    if (PH == 6 && first) { a.dbe2[c] += (float)Bq2[c]; a.dg2[c] += (float)Bq2[E + c]; }
+  }
+  if (PH >= 7) for (int c = tid; c < EH; c += kT) {
+    q1[c] = (float)(Bq1[c] / cnt1);
+    q1[EH + c] = (float)(Bq1[EH + c] / cnt1);
+    if (first) { a.dbe1[c] += (float)Bq1[c]; a.dg1[c] += (float)Bq1[EH + c]; }
+  }
+  for (int i = tid; i < NPAIR; i += kT) accW[i] = 0.f;
+  for (int i = tid; i < 2 * MAXCH; i += kT) sacc[i] = 0.0;
+  __syncthreads();
+
+  const float *A1 = cf1, *C1 = cf1 + EH, *mu1 = cf1 + 2 * EH, *r1 = cf1 + 3 * EH;
+  const float *A2 = cf2, *C2 = cf2 + E, *mu2 = cf2 + 2 * E, *r2 = cf2 + 3 * E;
+  const float *A3 = cf3, *C3 = cf3 + C, *mu3 = cf3 + 2 * C, *r3 = cf3 + 3 * C;
+
+  const int ntiles = (a.R + kT - 1) / kT;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r = tile * kT + tid;
+    const bool act = r < a.R;
+    int n = 0, t = 0, b = 0;
+    if (act) {
+      n = r % N;
+      const int bt = r / N;
+      t = bt % T;
+      b = bt / T;
+    }
+    float* c2t = a.c2raw + (size_t)tile * EL2 * kT + tid;     // + k*kT
+    float* z3t = a.z3raw + (size_t)tile * C * kT + tid;       // + c*kT
+    float* dn2t = a.dn2 + (size_t)tile * EL2 * kT + tid;
+    float* dn1t = a.dn1 + (size_t)tile * NL1 * kT + tid;
+
+    // ---- x and conv1 where the phase needs them ----
+    float x[P], c1[NL1];
+    constexpr bool NEED_C1 = PH == 0 || PH == 1 || PH == 6 || PH == 7;
+    if (NEED_C1 || PH == 3) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) x[i] = 0.f;
+      if (act && (NEED_C1 || !tr)) {
+        const float* xp = a.X + ((size_t)(b * N + n) * T + t) * P;
+#pragma unroll
+        for (int i = 0; i < P; ++i) x[i] = xp[i];
+      }
+      if (NEED_C1 || !tr) conv1_row<D>(W1, x, c1);
+    }
+
+    if constexpr (PH == 0) {
+#pragma unroll
+      for (int ch = 0; ch < EH; ++ch) {
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int p = 0; p < L1; ++p) {
+          const float v = act ? c1[ch * L1 + p] : 0.f;
+          s += v;
+          ss = fmaf(v, v, ss);
+        }
+        stat_add_f(sacc, ch, s);
+        stat_add_f(sacc, EH + ch, ss);
+      }
+    } else if constexpr (PH == 1) {
+      float a1[NL1], c2[EL2];
+#pragma unroll
+      for (int i = 0; i < NL1; ++i) a1[i] = fmaxf(fmaf(A1[i / L1], c1[i], C1[i / L1]), 0.f);
+      conv2_row<D>(W2, a1, c2);
+#pragma unroll
+      for (int k = 0; k < EL2; ++k) c2t[k * kT] = c2[k];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int p = 0; p < L2; ++p) {
+          const float v = act ? c2[e * L2 + p] : 0.f;
+          s += v;
+          ss = fmaf(v, v, ss);
+        }
+        stat_add_f(sacc, e, s);
+        stat_add_f(sacc, E + e, ss);
+      }
+    } else if constexpr (PH == 2 || PH == 3) {
+      float z[C];
+      if (PH == 2 || !tr) {
+        float a2[EL2];
+        if (PH == 2) {
+#pragma unroll
+          for (int k = 0; k < EL2; ++k) a2[k] = fmaxf(fmaf(A2[k / L2], c2t[k * kT], C2[k / L2]), 0.f);
+        } else {                 // eval forward: whole chain in one pass (no stored intermediates)
+          float a1[NL1], c2[EL2];
+#pragma unroll
+          for (int i = 0; i < NL1; ++i) a1[i] = fmaxf(fmaf(A1[i / L1], c1[i], C1[i / L1]), 0.f);
+          conv2_row<D>(W2, a1, c2);
+#pragma unroll
+          for (int k = 0; k < EL2; ++k) a2[k] = fmaxf(fmaf(A2[k / L2], c2[k], C2[k / L2]), 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float acc = b3[c];
+#pragma unroll
+          for (int k = 0; k < EL2; ++k) acc = fmaf(W3[c * EL2 + k], a2[k], acc);
+          z[c] = acc;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = z3t[c * kT];
+      }
+      if constexpr (PH == 2) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          z3t[c * kT] = z[c];
+          const float v = act ? z[c] : 0.f;
+          stat_add_f(sacc, c, v);
+          stat_add_f(sacc, C + c, v * v);
+        }
+      } else if (act) {
+        float* hr = a.h + (size_t)r * C;
+        const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
+        const float* pe = stage + t * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) hr[c] = (fmaf(A3[c], z[c], C3[c]) + pe[c]) * keep_scale_f(a, kbase + c);
+      }
+    } else if constexpr (PH == 4) {
+      const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float dhn = 0.f, zh = 0.f;
+        if (act) {
+          dhn = a.dh[(size_t)r * C + c] * keep_scale_f(a, kbase + c);
+          zh = (z3t[c * kT] - mu3[c]) * r3[c];
+        }
+        stat_add_f(sacc, c, dhn);
+        stat_add_f(sacc, C + c, dhn * zh);
+      }
+    } else if constexpr (PH == 5) {
+      float* sdz = stage;                 // [C][kTP]
+      float* sa2 = stage + C * kTP;       // [EL2][kTP]
+      float dz[C], a2[EL2], c2[EL2];
+      const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float v = 0.f;
+        if (act) {
+          const float dhn = a.dh[(size_t)r * C + c] * keep_scale_f(a, kbase + c);
+          const float zh = (z3t[c * kT] - mu3[c]) * r3[c];
+          v = A3[c] * (dhn - q3[c] - zh * q3[C + c]);
+        }
+        dz[c] = v;
+        sdz[c * kTP + tid] = v;
+      }
+#pragma unroll
+      for (int k = 0; k < EL2; ++k) {
+        c2[k] = act ? c2t[k * kT] : 0.f;
+        a2[k] = act ? fmaxf(fmaf(A2[k / L2], c2[k], C2[k / L2]), 0.f) : 0.f;
+        sa2[k * kTP + tid] = a2[k];
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        float s = 0.f, sh = 0.f;
+#pragma unroll
+        for (int p = 0; p < L2; ++p) {
+          const int k = e * L2 + p;
+          float v = 0.f;
+          if (a2[k] > 0.f) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) v = fmaf(dz[c], W3[c * EL2 + k], v);
+          }
+          dn2t[k * kT] = v;
+          s += v;
+          sh = fmaf(v, (c2[k] - mu2[e]) * r2[e], sh);
+        }
+        stat_add_f(sacc, e, s);
+        stat_add_f(sacc, E + e, sh);
+      }
+      __syncthreads();
+      pair_reduce_f<C * EL2 + C>(accW, [&](int pair, int r4) {
+        if (pair >= C * EL2) {
+          const float4 d = ld4(sdz + (pair - C * EL2) * kTP + r4);
+          return d.x + d.y + d.z + d.w;
+        }
+        const int c = pair / EL2, k = pair - c * EL2;
+        return dot4(ld4(sdz + c * kTP + r4), ld4(sa2 + k * kTP + r4));
+      });
+      __syncthreads();
+    } else if constexpr (PH == 6) {
+      float* sdc = stage;                 // [EL2][kTP]
+      float* sa1 = stage + EL2 * kTP;     // [NL1][kTP]
+      float dc2[EL2], a1[NL1];
+#pragma unroll
+      for (int k = 0; k < EL2; ++k) {
+        const int e = k / L2;
+        float v = 0.f;
+        if (act) {
+          const float ch2 = (c2t[k * kT] - mu2[e]) * r2[e];
+          v = A2[e] * (dn2t[k * kT] - q2[e] - ch2 * q2[E + e]);
+        }
+        dc2[k] = v;
+        sdc[k * kTP + tid] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < NL1; ++i) {
+        a1[i] = act ? fmaxf(fmaf(A1[i / L1], c1[i], C1[i / L1]), 0.f) : 0.f;
+        sa1[i * kTP + tid] = a1[i];
+      }
+#pragma unroll
+      for (int ch = 0; ch < EH; ++ch) {
+        float s = 0.f, sh = 0.f;
+#pragma unroll
+        for (int q = 0; q < L1; ++q) {
+          float v = 0.f;
+          if (a1[ch * L1 + q] > 0.f) {
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+#pragma unroll
+              for (int j = 0; j < K; ++j) {
+                const int p = q - j + 1;
+                if (p >= 0 && p < L2) v = fmaf(dc2[e * L2 + p], W2[(e * EH + ch) * K + j], v);
+              }
+          }
+          dn1t[(ch * L1 + q) * kT] = v;
+          s += v;
+          sh = fmaf(v, (c1[ch * L1 + q] - mu1[ch]) * r1[ch], sh);
+        }
+        stat_add_f(sacc, ch, s);
+        stat_add_f(sacc, EH + ch, sh);
+      }
+      __syncthreads();
+      pair_reduce_f<E * EH * K>(accW, [&](int pair, int r4) {
+        const int j = pair % K, ech = pair / K, ch = ech % EH, e = ech / EH;
+        float acc = 0.f;
+#pragma unroll
+        for (int p = 0; p < L2; ++p) {
+          const int q = p + j - 1;
+          if (q >= 0 && q < L1) acc += dot4(ld4(sdc + (e * L2 + p) * kTP + r4), ld4(sa1 + (ch * L1 + q) * kTP + r4));
+        }
+        return acc;
+      });
+      __syncthreads();
+    } else if constexpr (PH == 7) {
+      float* sdc = stage;                 // [NL1][kTP]
+      float* sx = stage + NL1 * kTP;      // [P][kTP]
+#pragma unroll
+      for (int i = 0; i < NL1; ++i) {
+        const int ch = i / L1;
+        float v = 0.f;
+        if (act) {
+          const float ch1 = (c1[i] - mu1[ch]) * r1[ch];
+          v = A1[ch] * (dn1t[i * kT] - q1[ch] - ch1 * q1[EH + ch]);
+        }
+        sdc[i * kTP + tid] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < P; ++i) sx[i * kTP + tid] = x[i];
+      __syncthreads();
+      pair_reduce_f<EH * K>(accW, [&](int pair, int r4) {
+        const int j = pair % K, ch = pair / K;
+        float acc = 0.f;
+#pragma unroll
+        for (int p = 0; p < L1; ++p) {
+          const int q = p + j - D::pad1;
+          if (q >= 0 && q < P) acc += dot4(ld4(sdc + (ch * L1 + p) * kTP + r4), ld4(sx + q * kTP + r4));
+        }
+        return acc;
+      });
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  constexpr int nstat = PH == 0 ? EH : PH == 1 ? E : PH == 2 ? C : PH == 4 ? C : PH == 5 ? E : PH == 6 ? EH : 0;
+  if (nstat) {
+    double* dst = PH == 0 ? a.st : PH == 1 ? a.st + 2 * EH : PH == 2 ? a.st + 2 * (EH + E) : PH == 4 ? Bq3 : PH == 5 ? Bq2 : Bq1;
+    for (int i = tid; i < 2 * nstat; i += kT) atomicAdd(&dst[i], sacc[i]);
+  }
+  if (PH == 5) {
+    for (int i = tid; i < C * EL2; i += kT) atomicAdd(&a.dW3[i], accW[i]);
+    for (int i = tid; i < C; i += kT) atomicAdd(&a.db3[i], accW[C * EL2 + i]);
+  } else if (PH == 6) {
+    for (int i = tid; i < E * EH * K; i += kT) atomicAdd(&a.dW2[i], accW[i]);
+  } else if (PH == 7) {
+    for (int i = tid; i < EH * K; i += kT) atomicAdd(&a.dW1[i], accW[i]);
+  }
+}
+
+template <class D, int PH>
+size_t stage_bytes(int T) {
+  size_t fl = 0;
+  if (PH == 3) fl = (size_t)T * D::C;
+  if (PH == 5) fl = (size_t)(D::C + D::EL2) * kTP;
+  if (PH == 6) fl = (size_t)(D::EL2 + D::NL1) * kTP;
+  if (PH == 7) fl = (size_t)(D::NL1 + D::P) * kTP;
+  return fl * 4;
+}
+
+const int kProfOfF[8] = {kProfEncF1, kProfEncF2, kProfEncF3, kProfEncF4, kProfEncB1, kProfEncB2, kProfEncB3, kProfEncB4};
+
+int sms_f() {
+  static int v = 0;
+  if (!v) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    v = n;
+  }
+  return v;
+}
+
+template <class D, int PH>
+void launch_one(const EncArgs& a, cudaStream_t s) {
+  const size_t smem = stage_bytes<D, PH>(a.T);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_enc_fast<D, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  const int ntiles = (a.R + kT - 1) / kT;
+  int per_sm = smem > 48 * 1024 ? 2 : smem > 24 * 1024 ? 3 : 4;
+  int grid = sms_f() * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  ProfScope ps(kProfOfF[PH], s);
+  k_enc_fast<D, PH><<<grid, kT, smem, s>>>(a);
+}
+
+template <class D>
+bool matches(const EncArgs& a) {
+  return a.P == D::P && a.K == D::K && a.EH == D::EH && a.E == D::E && a.C == D::C &&
+         (size_t)a.T * D::C * 4 <= 100 * 1024;
+}
+
+template <class D>
+void run(const EncArgs& a, bool backward, cudaStream_t s) {
+  if (!backward) {
+    if (a.training) {
+      launch_one<D, 0>(a, s);
+      launch_one<D, 1>(a, s);
+      launch_one<D, 2>(a, s);
+    }
+    launch_one<D, 3>(a, s);
+  } else {
+    launch_one<D, 4>(a, s);
+    launch_one<D, 5>(a, s);
+    launch_one<D, 6>(a, s);
+    launch_one<D, 7>(a, s);
+  }
+}
+
+// configs/hparams.py FC_STGNN sets with register-sized rows (FD001 / N-CMAPSS use the generic kernels)
+using D_FD004 = EncDims<2, 2, 8, 6, 16>;   // hparams.py:149-151  (S1)
+using D_S2 = EncDims<1, 2, 8, 6, 14>;      // BASELINE synthetic   (S2)
+using D_FD002 = EncDims<1, 2, 8, 12, 16>;  // hparams.py:69-71
+using D_FD003 = EncDims<1, 2, 8, 6, 48>;   // hparams.py:109-111
+
+}  // namespace
+
+bool encoder_fast_available(const EncArgs& a) {
+  return matches<D_FD004>(a) || matches<D_S2>(a) || matches<D_FD002>(a) || matches<D_FD003>(a);
+}
+
+int launch_encoder_fast(const EncArgs& a, bool backward, cudaStream_t s) {
+  if (matches<D_FD004>(a)) run<D_FD004>(a, backward, s);
+  else if (matches<D_S2>(a)) run<D_S2>(a, backward, s);
+  else if (matches<D_FD002>(a)) run<D_FD002>(a, backward, s);
+  else if (matches<D_FD003>(a)) run<D_FD003>(a, backward, s);
+  else return -2;
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+}  // namespace stg

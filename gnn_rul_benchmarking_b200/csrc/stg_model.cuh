@@ -24,6 +24,8 @@ struct EncArgs {
   int training;
   float momentum, eps;
   double* st;                 // stats scratch, see enc_stat_off()
+  // fast path only: raw activations / masked gradients kept between phases, [tile][feature][256]
+  float *c2raw, *z3raw, *dn2, *dn1;
   float* h;                   // [R, C] output of the forward
   const float* dh;            // [R, C] gradient wrt h
   float *dW1, *dW2, *dW3, *db3, *dg1, *dbe1, *dg2, *dbe2, *dg3, *dbe3;
@@ -35,6 +37,9 @@ inline __host__ __device__ int enc_stats_doubles(int EH, int E, int C) { return 
 int plan_encoder(EncArgs& a, size_t* smem_fwd, size_t* smem_bwd, char* err, size_t errlen);
 int launch_encoder_forward(const EncArgs& a, size_t smem, cudaStream_t s);
 int launch_encoder_backward(const EncArgs& a, size_t smem, cudaStream_t s);
+// compile-time-dimension variants (stg_encoder_fast.cu) for the register-sized hyper-parameter sets
+bool encoder_fast_available(const EncArgs& a);
+int launch_encoder_fast(const EncArgs& a, bool backward, cudaStream_t s);
 
 // ---- FC head (Model.py:30-39,83) + MSE -------------------------------------------------------
 struct HeadArgs {

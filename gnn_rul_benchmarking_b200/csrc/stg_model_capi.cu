@@ -11,10 +11,11 @@ namespace stg {
 namespace {
 
 struct Ws {            // byte offsets into the caller's workspace
-  size_t h, dh, feat, dfeat, yp[2], dxp[2], z1, d1, dbl, xmom, bst[2], est, loss, dbl_end, total;
+  size_t h, dh, feat, dfeat, yp[2], dxp[2], z1, d1, c2raw, z3raw, dn2, dn1, dbl, xmom, bst[2], est, loss, dbl_end,
+      total;
 };
 struct Geo {
-  int C, J, F, L[2], M[2], R;
+  int C, J, F, L[2], M[2], R, EL2, NL1;
   size_t fsz[2];
 };
 
@@ -25,6 +26,12 @@ int geometry(const stg_model_dims& d, Geo& g) {
   g.C = 2 * d.H;
   g.J = 2 * d.H;
   g.R = d.B * d.T * d.N;
+  {
+    const int pad1 = d.K / 2, L1 = d.P + 2 * pad1 - d.K + 1, L2 = L1 + 2 - d.K + 1;
+    if (L1 < 1 || L2 < 1) return -1;
+    g.EL2 = d.E * L2;
+    g.NL1 = d.EH * L1;
+  }
   g.F = 0;
   for (int z = 0; z < STG_MAX_BLOCKS; ++z) {
     if (d.w[z] < 1 || d.stride[z] < 1 || d.T < d.w[z]) return -1;
@@ -47,6 +54,13 @@ void layout(const stg_model_dims& d, const Geo& g, Ws& w) {
   for (int z = 0; z < 2; ++z) { w.dxp[z] = o; o += rc; }
   w.z1 = o; o += al((size_t)d.B * g.J * 4);
   w.d1 = o; o += al((size_t)d.B * g.J * 4);
+  {
+    const size_t tiles = ((size_t)g.R + 255) / 256;
+    w.c2raw = o; o += al(tiles * g.EL2 * 256 * 4);
+    w.z3raw = o; o += al(tiles * g.C * 256 * 4);
+    w.dn2 = o; o += al(tiles * g.EL2 * 256 * 4);
+    w.dn1 = o; o += al(tiles * g.NL1 * 256 * 4);
+  }
   w.dbl = o;                                                   // ---- zeroed at the start of every forward
   w.xmom = o; o += al((size_t)2 * d.T * g.C * 8);
   for (int z = 0; z < 2; ++z) { w.bst[z] = o; o += al((size_t)STG_BLOCK_STATS_DOUBLES(g.C, d.H) * 8); }
@@ -103,6 +117,8 @@ int build_ctx(Ctx& c, const stg_model_dims* dp, const stg_model_params* pp, cons
   e.st = (double*)(base + c.w.est);
   e.h = (float*)(base + c.w.h);
   e.dh = (const float*)(base + c.w.dh);
+  e.c2raw = (float*)(base + c.w.c2raw); e.z3raw = (float*)(base + c.w.z3raw);
+  e.dn2 = (float*)(base + c.w.dn2); e.dn1 = (float*)(base + c.w.dn1);
   if (gp) {
     e.dW1 = gp->conv1_w; e.dW2 = gp->conv2_w; e.dW3 = gp->lin_w; e.db3 = gp->lin_b;
     e.dg1 = gp->bn1.weight; e.dbe1 = gp->bn1.bias; e.dg2 = gp->bn2.weight; e.dbe2 = gp->bn2.bias;
