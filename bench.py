@@ -67,6 +67,18 @@ def algorithmic_bytes(cfg, B):
 KERNEL_BYTES_KIND = {"k_block_fwd": "fwd", "k_block_bwd": "bwd"}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/ncu_summary.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        with open(p) as fh:
+            k = json.load(fh)["kernels"][kernel]
+        return k["dram_bytes_read"] + k["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -178,7 +190,6 @@ def run_native(args):
 
     from gnn_rul_benchmarking_b200 import _lib
     from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
-    from gnn_rul_benchmarking_b200.dp import FlatGradAllReduce
     _lib.load()
 
     cfg = model_cfg(args.workload)
@@ -187,7 +198,8 @@ def run_native(args):
     torch.manual_seed(0)
     alg = get_algorithm_class("FC_STGNN")(cfg, HPARAMS, dev).to(dev)
     alg.train()
-    dp = FlatGradAllReduce(alg.model) if world > 1 else None
+    if world > 1:
+        alg.attach_data_parallel()      # one NCCL all-reduce of the flat gradient buffer per step
 
     g = torch.Generator().manual_seed(1234 + rank)
     nbuf = 4
@@ -254,7 +266,9 @@ def run_native(args):
         nbytes = ab[KERNEL_BYTES_KIND[name]]
         achieved = nbytes / avg_s / 1e9
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "peak_source": peak_kind,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "algorithmic_bytes": nbytes,
+                "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(name) if args.workload == "S1" and B == 256 else None,
+                "algorithmic_bytes": nbytes,
                 "avg_launch_us": avg_s * 1e6,
                 "share_of_lib_time": tot_ms / max(1e-9, sum(t for t, _ in kern.values())),
                 "kernels_us": {k: round(1e3 * t / n2, 2) for k, (t, n2) in kern.items()}}

@@ -106,41 +106,104 @@ static size_t carve_bytes(int CP, int HP, int rows_max, int C, int wpc, int slot
   return 16 + f * 4;
 }
 
-// BN0 statistics (batch or running), folded projection [Wm | Wtheta.diag(g0 r0)]^T and biases.
-template <int CP, int HP, bool TRAIN>
-STG_DEVINL void block_prologue(const BlkArgs& a, const BlkDev& k, Carve<CP, HP>& sm, bool update_running) {
-  constexpr int CPH = CP + HP;
-  const int C = a.C, T = a.T, H = k.H, tid = threadIdx.x, nt = blockDim.x;
-  const int M = k.w * a.N;
+// ------------------------------------------------------------------------------------------
+// Per-block coefficient table (training): everything the main kernels' prologues need that depends
+// only on the parameters and the BN0 batch moments, computed ONCE per launch sequence instead of
+// once per CTA:   mu0[CP] r0[CP] a0[CP] c0[CP] biasc[CPH] pw[4] WcT[CP*CPH] cnt[T]
+// grid (nblk), block 256.  Also updates the BN0 running statistics.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline int coef_floats(int CP, int HP, int T) { return 4 * CP + (CP + HP) + 4 + CP * (CP + HP) + T; }
+
+__global__ void __launch_bounds__(256) k_block_prep(const BlkArgs a, int CP, int HP) {
+  __shared__ double ssum[48], ssq[48];
+  __shared__ float sa0[48], sc0[48];
+  const BlkDev& k = a.b[blockIdx.x];
+  const int C = a.C, T = a.T, H = k.H, tid = threadIdx.x, CPH = CP + HP;
+  float* tab = k.coef;
+  float* mu0 = tab; float* r0 = mu0 + CP; float* a0 = r0 + CP; float* c0 = a0 + CP;
+  float* biasc = c0 + CP; float* pw = biasc + CPH; float* WcT = pw + 4; float* cnt = WcT + CP * CPH;
+  if (tid < 48) { ssum[tid] = 0.0; ssq[tid] = 0.0; }
+  __syncthreads();
+  // weighted moments of x over time: thread (c, slice of t)
+  {
+    const int c = tid % CP, sl = tid / CP, nsl = 256 / CP;
+    if (c < C && sl < nsl) {
+      double s = 0.0, q = 0.0;
+      for (int t = sl; t < T; t += nsl) {
+        const int cn = cover_count(t, k.w, k.stride, k.L);
+        if (cn) {
+          s += cn * a.xmom[t * C + c];
+          q += cn * a.xmom[(size_t)T * C + t * C + c];
+        }
+      }
+      atomicAdd(&ssum[c], s);
+      atomicAdd(&ssq[c], q);
+    }
+  }
+  for (int t = tid; t < T; t += 256) cnt[t] = (float)cover_count(t, k.w, k.stride, k.L);
+  if (tid < 4) pw[tid] = powf(k.decay, (float)tid);
+  __syncthreads();
   if (tid < CP) {
     const int c = tid;
     float mean = 0.f, r = 0.f, av = 0.f, cv = 0.f;
     if (c < C) {
-      double m, var;
-      if (TRAIN) {
-        double sum = 0.0, sq = 0.0;
-        for (int t = 0; t < T; ++t) {
-          const int cnt = cover_count(t, k.w, k.stride, k.L);
-          if (cnt) {
-            sum += cnt * a.xmom[t * C + c];
-            sq += cnt * a.xmom[(size_t)T * C + t * C + c];
-          }
-        }
-        const double R = (double)a.B * k.L * M;
-        m = sum / R;
-        var = sq / R - m * m;
-        if (var < 0.0) var = 0.0;
-        if (update_running) {
-          const double unb = R > 1.0 ? var * R / (R - 1.0) : var;
-          k.rm0[c] = (1.f - a.momentum) * k.rm0[c] + a.momentum * (float)m;
-          k.rv0[c] = (1.f - a.momentum) * k.rv0[c] + a.momentum * (float)unb;
-        }
-      } else {
-        m = k.rm0[c];
-        var = k.rv0[c];
-      }
+      const double R = (double)a.B * k.L * k.w * a.N;
+      const double m = ssum[c] / R;
+      double var = ssq[c] / R - m * m;
+      if (var < 0.0) var = 0.0;
+      const double unb = R > 1.0 ? var * R / (R - 1.0) : var;
+      k.rm0[c] = (1.f - a.momentum) * k.rm0[c] + a.momentum * (float)m;
+      k.rv0[c] = (1.f - a.momentum) * k.rv0[c] + a.momentum * (float)unb;
       mean = (float)m;
       r = (float)(1.0 / sqrt(var + (double)a.eps));
+      av = k.g0[c] * r;
+      cv = k.b0[c] - av * mean;
+    }
+    mu0[c] = mean; r0[c] = r; a0[c] = av; c0[c] = cv;
+    sa0[c] = av; sc0[c] = cv;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < CP * CPH; idx += 256) {
+    const int c = idx / CPH, o = idx % CPH;
+    float v = 0.f;
+    if (c < C) {
+      if (o < C) v = k.Wm[o * C + c];
+      else if (o >= CP && o - CP < H) v = k.Wt[(o - CP) * C + c] * sa0[c];
+    }
+    WcT[idx] = v;
+  }
+  for (int o = tid; o < CPH; o += 256) {
+    float v = 0.f;
+    if (o < C) v = k.bm[o];
+    else if (o >= CP && o - CP < H) {
+      const float* wr = k.Wt + (o - CP) * C;
+      for (int c = 0; c < C; ++c) v += wr[c] * sc0[c];
+    }
+    biasc[o] = v;
+  }
+}
+
+// BN0 statistics (batch or running), folded projection [Wm | Wtheta.diag(g0 r0)]^T and biases.
+template <int CP, int HP, bool TRAIN>
+STG_DEVINL void block_prologue(const BlkArgs& a, const BlkDev& k, Carve<CP, HP>& sm) {
+  constexpr int CPH = CP + HP;
+  const int C = a.C, H = k.H, tid = threadIdx.x, nt = blockDim.x;
+  if (TRAIN) {
+    // table written by k_block_prep: mu0 r0 a0 c0 biasc | pw | WcT   (smem: ... biasc bn1c pw WcT)
+    const float* tab = k.coef;
+    for (int i = tid; i < 4 * CP + CPH; i += nt) sm.mu0[i] = tab[i];
+    if (tid < 4) sm.pw[tid] = tab[4 * CP + CPH + tid];
+    const float4* src = reinterpret_cast<const float4*>(tab + 4 * CP + CPH + 4);
+    float4* dst = reinterpret_cast<float4*>(sm.WcT);
+    for (int i = tid; i < CP * CPH / 4; i += nt) dst[i] = src[i];
+    return;
+  }
+  if (tid < CP) {
+    const int c = tid;
+    float mean = 0.f, r = 0.f, av = 0.f, cv = 0.f;
+    if (c < C) {
+      mean = k.rm0[c];
+      r = (float)(1.0 / sqrt((double)k.rv0[c] + (double)a.eps));
       av = k.g0[c] * r;
       cv = k.b0[c] - av * mean;
     }
@@ -231,7 +294,7 @@ __global__ void __launch_bounds__(256) k_block_fwd(const BlkArgs a, int rows_max
   const int shift = stage_floats_tma(sm.xs, a.x + ((size_t)b * T + t_lo) * N * C, rows * C, sm.bar, tid);
   const float* xs = sm.xs + shift;
 
-  block_prologue<CP, HP, TRAIN>(a, k, sm, chunk == 0 && b == 0);
+  block_prologue<CP, HP, TRAIN>(a, k, sm);
   // BN1 coefficients (eval only): yn = a1*y + c1
   if (!TRAIN && tid < HP) {
     float a1 = 0.f, c1 = 0.f;
@@ -488,7 +551,7 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
   const int shift = stage_floats_tma(sm.xs, a.x + ((size_t)b * T + t_lo) * N * C, rows * C, sm.bar, tid);
   const float* xs = sm.xs + shift;
 
-  block_prologue<CP, HP, true>(a, k, sm, false);
+  block_prologue<CP, HP, true>(a, k, sm);
   // raw Wm [o][c] and Wtheta [h][c] for the transposed products
   for (int idx = tid; idx < CP * CP; idx += nt) {
     const int o = idx / CP, c = idx % CP;
@@ -724,31 +787,20 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
 // backward finalize: dx = sum_blk dxp_blk - r0*cnt(t)*(m1 + Xhat*m2); BN affine grads.
 // grid (ceil(B*T*N*C/256)); dynamic smem: nblk * (4*C + T) floats
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_block_bwd_fin(const BlkArgs a) {
+__global__ void __launch_bounds__(256) k_block_bwd_fin(const BlkArgs a, int CP) {
   extern __shared__ float smf[];
   const int C = a.C, T = a.T, N = a.N;
   const int per = 4 * C + T;
   for (int z = 0; z < a.nblk; ++z) {
     const BlkDev& k = a.b[z];
     float* tb = smf + z * per;
-    const int M = k.w * N;
-    const double R = (double)a.B * k.L * M;
+    const double R = (double)a.B * k.L * k.w * N;
+    const float* tab = k.coef;                 // mu0[CP] r0[CP] ...
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      double sum = 0.0, sq = 0.0;
-      for (int t = 0; t < T; ++t) {
-        const int cnt = cover_count(t, k.w, k.stride, k.L);
-        if (cnt) {
-          sum += cnt * a.xmom[t * C + c];
-          sq += cnt * a.xmom[(size_t)T * C + t * C + c];
-        }
-      }
-      const double m = sum / R;
-      double var = sq / R - m * m;
-      if (var < 0.0) var = 0.0;
-      const float r0 = (float)(1.0 / sqrt(var + (double)a.eps));
+      const float r0 = tab[CP + c];
       const float g0 = k.g0[c];
       const double sb = k.stats[4 * k.H + c], sg = k.stats[4 * k.H + C + c];
-      tb[c] = (float)m;
+      tb[c] = tab[c];
       tb[C + c] = r0;
       tb[2 * C + c] = r0 * (float)(g0 * sb / R);
       tb[3 * C + c] = r0 * (float)(g0 * sg / R);
@@ -766,18 +818,41 @@ __global__ void __launch_bounds__(256) k_block_bwd_fin(const BlkArgs a) {
   }
   __syncthreads();
   const long long total = (long long)a.B * T * N * C;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int c = (int)(e % C);
-  const int t = (int)((e / ((long long)N * C)) % T);
-  const float xv = a.x[e];
-  float v = 0.f;
-  for (int z = 0; z < a.nblk; ++z) {
-    const float* tb = smf + z * per;
-    const float xh = (xv - tb[c]) * tb[C + c];
-    v += a.b[z].dxp[e] - tb[4 * C + t] * (tb[2 * C + c] + xh * tb[3 * C + c]);
+  for (long long e4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; e4 * 4 < total;
+       e4 += (long long)gridDim.x * blockDim.x) {
+    const long long e0 = e4 * 4;
+    float xv[4], out[4];
+    const int nv = (int)((total - e0) < 4 ? (total - e0) : 4);
+    if (nv == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(a.x + e0);
+      xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+    } else {
+      for (int u = 0; u < nv; ++u) xv[u] = a.x[e0 + u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) out[u] = 0.f;
+    for (int z = 0; z < a.nblk; ++z) {
+      const float* tb = smf + z * per;
+      float dv[4];
+      if (nv == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(a.b[z].dxp + e0);
+        dv[0] = v.x; dv[1] = v.y; dv[2] = v.z; dv[3] = v.w;
+      } else {
+        for (int u = 0; u < nv; ++u) dv[u] = a.b[z].dxp[e0 + u];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nv) {
+          const long long e = e0 + u;
+          const int c = (int)(e % C);
+          const int t = (int)((e / ((long long)N * C)) % T);
+          const float xh = (xv[u] - tb[c]) * tb[C + c];
+          out[u] += dv[u] - tb[4 * C + t] * (tb[2 * C + c] + xh * tb[3 * C + c]);
+        }
+    }
+    if (nv == 4) *reinterpret_cast<float4*>(a.dx + e0) = make_float4(out[0], out[1], out[2], out[3]);
+    else for (int u = 0; u < nv; ++u) a.dx[e0 + u] = out[u];
   }
-  a.dx[e] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -934,6 +1009,10 @@ int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
     for (int z = 0; z < a.nblk; ++z)
       cudaMemsetAsync(a.b[z].stats, 0, sizeof(double) * (4 * a.b[z].H + 2 * a.C), s);
     {
+      ProfScope ps(kProfBlkPrep, s);
+      k_block_prep<<<a.nblk, 256, 0, s>>>(a, p.CP, p.HP);
+    }
+    {
       ProfScope ps(kProfFwdMain, s);
       v->fwd_train<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max, p.wpc_f, slot);
     }
@@ -976,7 +1055,10 @@ int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   }
   const long long tot = (long long)a.B * a.T * a.N * a.C;
   ProfScope ps(kProfBwdFin, s);
-  k_block_bwd_fin<<<(unsigned)((tot + 255) / 256), 256, a.nblk * (4 * a.C + a.T) * sizeof(float), s>>>(a);
+  long long gfin = (tot / 4 + 255) / 256;
+  if (gfin > 148 * 8) gfin = 148 * 8;
+  if (gfin < 1) gfin = 1;
+  k_block_bwd_fin<<<(unsigned)gfin, 256, a.nblk * (4 * a.C + a.T) * sizeof(float), s>>>(a, p.CP);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

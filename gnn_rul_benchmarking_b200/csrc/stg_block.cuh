@@ -16,6 +16,7 @@ struct BlkDev {
   long long out_bs;
   float* yp;
   double* stats;
+  float* coef;      // training: coefficient table written by k_block_prep (lives behind stats)
   // backward only
   const float* dout;
   long long dout_bs;

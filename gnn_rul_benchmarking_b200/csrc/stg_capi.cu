@@ -43,6 +43,7 @@ static int fill_args(BlkArgs& a, const float* x, int B, int T, int N, int C, con
     k.Wm = d.Wm; k.bm = d.bm; k.g0 = d.bn0_w; k.b0 = d.bn0_b; k.rm0 = d.bn0_rm; k.rv0 = d.bn0_rv;
     k.Wt = d.Wt; k.bt = d.bt; k.g1 = d.bn1_w; k.b1 = d.bn1_b; k.rm1 = d.bn1_rm; k.rv1 = d.bn1_rv;
     k.out = d.out; k.out_bs = d.out_bstride; k.yp = d.yp; k.stats = d.stats;
+    k.coef = d.stats ? reinterpret_cast<float*>(d.stats + ((STG_BLOCK_SUMS_DOUBLES(C, d.H) + 1) / 2) * 2) : nullptr;
     if (gr) {
       const stg_block_grads& g = gr[z];
       if (!g.dout || !g.dWm || !g.dbm || !g.dbn0_w || !g.dbn0_b || !g.dWt || !g.dbt || !g.dbn1_w || !g.dbn1_b ||

@@ -78,7 +78,7 @@ STG_DEVINL int stage_floats_tma(float* dst16, const float* src, int nfl, uint64_
 enum ProfSlot {
   kProfXmoments = 0, kProfFwdMain, kProfFwdFin, kProfBwdStats, kProfBwdMain, kProfBwdFin,
   kProfEncF1, kProfEncF2, kProfEncF3, kProfEncF4, kProfEncB1, kProfEncB2, kProfEncB3, kProfEncB4,
-  kProfHeadFc1, kProfHeadTail, kProfHeadBwd1, kProfAdam, kProfZero, kProfSlots
+  kProfHeadFc1, kProfHeadTail, kProfHeadBwd1, kProfAdam, kProfZero, kProfBlkPrep, kProfSlots
 };
 // Records an event pair around the launches issued while the scope is alive (host-side no-op when
 // profiling is disabled).  Events go on the same stream as the kernels.

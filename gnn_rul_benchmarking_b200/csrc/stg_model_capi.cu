@@ -63,7 +63,7 @@ void layout(const stg_model_dims& d, const Geo& g, Ws& w) {
   }
   w.dbl = o;                                                   // ---- zeroed at the start of every forward
   w.xmom = o; o += al((size_t)2 * d.T * g.C * 8);
-  for (int z = 0; z < 2; ++z) { w.bst[z] = o; o += al((size_t)STG_BLOCK_STATS_DOUBLES(g.C, d.H) * 8); }
+  for (int z = 0; z < 2; ++z) { w.bst[z] = o; o += al((size_t)STG_BLOCK_STATS_DOUBLES(g.C, d.H, d.T) * 8); }
   w.est = o; o += al((size_t)enc_stats_doubles(d.EH, d.E, g.C) * 8);
   w.loss = o; o += al(16);
   w.dbl_end = o;
@@ -148,6 +148,7 @@ int build_ctx(Ctx& c, const stg_model_dims* dp, const stg_model_params* pp, cons
     k.out_bs = g.F;
     k.yp = (float*)(base + c.w.yp[z]);
     k.stats = (double*)(base + c.w.bst[z]);
+    k.coef = reinterpret_cast<float*>(k.stats + ((STG_BLOCK_SUMS_DOUBLES(g.C, d.H) + 1) / 2) * 2);
     k.dout = (const float*)(base + c.w.dfeat) + foff;
     k.dout_bs = g.F;
     k.dxp = (float*)(base + c.w.dxp[z]);

@@ -18,7 +18,7 @@ const char* kNames[kProfSlots] = {
     "k_xmoments", "k_block_fwd", "k_block_fwd_fin", "k_block_bwd_stats", "k_block_bwd", "k_block_bwd_fin",
     "k_encoder<F1>", "k_encoder<F2>", "k_encoder<F3>", "k_encoder<F4>",
     "k_encoder<B1>", "k_encoder<B2>", "k_encoder<B3>", "k_encoder<B4>",
-    "k_head_fc1", "k_head_tail", "k_head_bwd1", "k_adam", "k_zero"};
+    "k_head_fc1", "k_head_tail", "k_head_bwd1", "k_adam", "k_zero", "k_block_prep"};
 constexpr size_t kMaxPairs = 1 << 16;
 }  // namespace
 

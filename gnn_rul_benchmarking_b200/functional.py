@@ -34,6 +34,13 @@ def _check_dev(t: torch.Tensor, name: str) -> None:
         raise ValueError(f"{name} must be contiguous")
 
 
+def stats_doubles(C: int, H: int, T: int) -> int:
+    """STG_BLOCK_STATS_DOUBLES(C,H,T) of include/stgconv_b200.h."""
+    p16, p8 = (C + 15) // 16 * 16, (H + 7) // 8 * 8
+    coef = 4 * p16 + (p16 + p8) + 4 + p16 * (p16 + p8) + T
+    return (4 * H + 2 * C + 1) // 2 * 2 + (coef + 1) // 2
+
+
 def num_windows(T: int, w: int, s: int) -> int:
     return (T - w) // s + 1
 
@@ -79,7 +86,7 @@ class _GraphBlocks(torch.autograd.Function):
                 d.out_bstride = Ftot
                 if training:
                     yp = torch.empty(B, Ls[z], hp["w"] * N, hp["H"], device=x.device, dtype=torch.float32)
-                    st = torch.empty(4 * hp["H"] + 2 * Cc, device=x.device, dtype=torch.float64)
+                    st = torch.empty(stats_doubles(Cc, hp["H"], T), device=x.device, dtype=torch.float64)
                     d.yp, d.stats = yp.data_ptr(), st.data_ptr()
                     saved_yp.append(yp)
                     saved_stats.append(st)

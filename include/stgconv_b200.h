@@ -72,14 +72,23 @@ typedef struct stg_block_desc {
   float* out;         /* [B, L, N, H] with sample stride out_bstride (floats)              */
   int64_t out_bstride;/* >= L*N*H; lets two blocks write straight into the FC-head input   */
   float* yp;          /* training only: pre-BN Y' [B,L,w*N,H] (saved for backward)         */
-  double* stats;      /* training only: STG_BLOCK_STATS_DOUBLES(C,H) doubles of batch stats*/
+  double* stats;      /* training only: STG_BLOCK_STATS_DOUBLES(C,H,T) doubles of scratch  */
 } stg_block_desc;
 
 /* layout of stg_block_desc.stats (doubles):
  *   [0,H)        sum_R  Y'            [H,2H)      sum_R Y'^2          (forward)
  *   [2H,3H)      sum_R  dYn           [3H,4H)     sum_R dYn*Yhat      (backward)
- *   [4H,4H+C)    sum_R  dXhat         [4H+C,4H+2C) sum_R dXhat*Xhat   (backward)          */
-#define STG_BLOCK_STATS_DOUBLES(C, H) (4 * (H) + 2 * (C))
+ *   [4H,4H+C)    sum_R  dXhat         [4H+C,4H+2C) sum_R dXhat*Xhat   (backward)
+ *   then (16-byte aligned) the float coefficient table.                                  */
+#define STG_BLOCK_SUMS_DOUBLES(C, H) (4 * (H) + 2 * (C))
+/* ... followed by a float table of per-feature coefficients shared by the kernels of one launch
+ * sequence (BN0 mean / rstd, folded projection weights, cover counts), sized for the padded dims. */
+#define STG_PAD16(x) ((((x) + 15) / 16) * 16)
+#define STG_PAD8(x) ((((x) + 7) / 8) * 8)
+#define STG_BLOCK_COEF_FLOATS(C, H, T) \
+  (4 * STG_PAD16(C) + (STG_PAD16(C) + STG_PAD8(H)) + 4 + STG_PAD16(C) * (STG_PAD16(C) + STG_PAD8(H)) + (T))
+#define STG_BLOCK_STATS_DOUBLES(C, H, T) \
+  (((STG_BLOCK_SUMS_DOUBLES(C, H) + 1) / 2) * 2 + (STG_BLOCK_COEF_FLOATS(C, H, T) + 1) / 2)
 
 /* gradients of one block, device pointers; all are ACCUMULATED into (+=) except dxp. */
 typedef struct stg_block_grads {

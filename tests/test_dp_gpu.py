@@ -1,0 +1,56 @@
+"""2-GPU data parallel (NCCL): windows sharded across ranks, ONE all-reduce of the flat gradient
+buffer per step; replicas stay bit-identical and the first step equals the single-GPU step on the
+concatenated batch when BatchNorm sees the same statistics (eval of the averaged gradient)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
+    from gnn_rul_benchmarking_b200.configs import CONFIGS, TRAIN_PARAMS
+    torch.manual_seed(50 + rank)                       # different init per rank: the broadcast must fix it
+    alg = get_algorithm_class("FC_STGNN")(CONFIGS["FD004"], TRAIN_PARAMS, dev).to(dev)
+    alg.model.positional_encoding.dropout.p = 0.0
+    alg.train()
+    alg.attach_data_parallel()
+    g = torch.Generator().manual_seed(3)
+    X, y = torch.rand(16, 14, 50, generator=g), torch.rand(16, 1, generator=g)
+    losses = []
+    for it in range(3):
+        out = alg.update(X[rank::world].contiguous().to(dev), y[rank::world].contiguous().to(dev), it)
+        losses.append(out["loss"])
+    flat = alg.model.engine.flat["param"].clone()
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        q.put((losses, [t.cpu() for t in gathered]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_replicas_stay_identical():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    losses, params = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(l == l for l in losses)                 # finite
+    assert torch.equal(params[0], params[1])           # same averaged gradient -> same Adam update

@@ -1,0 +1,98 @@
+"""CPU: host-side logic -- config tables, algorithm registry, no-CPU-fallback behaviour, window
+sharding, and the data-parallel gradient exchange on world_size-2 gloo."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_configs_match_oracle_tables():
+    from gnn_rul_benchmarking_b200 import configs
+    from oracle import fc_stgnn_oracle as orc
+    assert configs.CONFIGS == orc.CONFIGS
+    assert configs.TRAIN_PARAMS == orc.TRAIN_HPARAMS
+    for name, cfg in configs.CONFIGS.items():
+        T, h, N = cfg["num_patch"], cfg["hidden_dim"], cfg["num_node"]
+        L = (T - 2) + 1 + (T - 2) // 2 + 1
+        assert cfg["num_windows"] == L, name                              # fc1 input = h * num_windows * N
+        k, P = cfg["encoder_conv_kernel"], cfg["patch_size"]
+        l1 = P + 2 * (k // 2) - k + 1
+        assert cfg["encoder_time_out"] == l1 + 2 - k + 1, name
+
+
+def test_algorithm_registry_and_error_behaviour():
+    from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
+    from gnn_rul_benchmarking_b200.configs import CONFIGS, TRAIN_PARAMS
+    with pytest.raises(NotImplementedError):          # algorithms.py:31-32
+        get_algorithm_class("NOPE")
+    alg = get_algorithm_class("FC_STGNN")(CONFIGS["FD001"], TRAIN_PARAMS, "cpu")
+    keys = set(alg.state_dict())
+    assert "model.MPNN1.graph_construction.mapping.weight" in keys and "model.fc.fc4.bias" in keys
+    assert "model.MPNN1.pre_relation" not in keys     # plain attribute in the reference (Model_Base.py:187)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        alg.update(torch.rand(2, 14, 50), torch.rand(2, 1), 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        alg.model(torch.rand(2, 14, 50))
+
+
+def test_mask_matrix_closed_form():
+    from gnn_rul_benchmarking_b200.fc_stgnn import Mask_Matrix
+    m = Mask_Matrix(3, 2, 0.7)
+    assert m.shape == (6, 6)
+    assert torch.allclose(m[:3, :3], torch.ones(3, 3)) and torch.allclose(m[:3, 3:], torch.full((3, 3), 0.7))
+
+
+def test_shard_indices_partition():
+    from gnn_rul_benchmarking_b200.dp import shard_indices
+    n, world = 1003, 4
+    parts = [list(shard_indices(n, r, world)) for r in range(world)]
+    assert len({len(p) for p in parts}) == 1                      # equal counts: no rank waits in a collective
+    flat = sorted(i for p in parts for i in p)
+    assert flat == list(range(1000))                               # tail dropped, no overlap
+    parts = [list(shard_indices(n, r, world, drop_tail=False)) for r in range(world)]
+    assert sorted(i for p in parts for i in p) == list(range(n))
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from gnn_rul_benchmarking_b200.dp import FlatGradAllReduce
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                                  # different init per rank: broadcast must fix it
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.BatchNorm1d(5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    hook = FlatGradAllReduce(net)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(7)
+    X, y = torch.rand(8, 6, generator=g), torch.rand(8, 1, generator=g)
+    Xr, yr = X[rank::world], y[rank::world]                        # window sharding
+    for _ in range(3):                                             # the reference's update order (algorithms.py:72-74)
+        loss = torch.nn.functional.mse_loss(net(Xr), yr)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        q.put((hook.n_allreduce, [t.tolist() for t in gathered]))
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n_ar, params = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert n_ar == 3                                               # exactly one collective per backward
+    assert torch.allclose(torch.tensor(params[0]), torch.tensor(params[1]), atol=1e-7)   # replicas stay identical
