@@ -15,6 +15,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace stg {
 
@@ -868,7 +869,8 @@ struct Variant {
 #define STG_VARIANT(CP, HP) \
   { CP, HP, k_block_fwd<CP, HP, true>, k_block_fwd<CP, HP, false>, k_block_bwd<CP, HP>, k_block_bwd_stats<HP> }
 static const Variant kVariants[] = {
-    STG_VARIANT(4, 4), STG_VARIANT(8, 4), STG_VARIANT(16, 8), STG_VARIANT(32, 16), STG_VARIANT(48, 24),
+    // same (CP, HP) set as the tensor-core path (stg_block_mma.cu): both read one coefficient table
+    STG_VARIANT(8, 8), STG_VARIANT(16, 8), STG_VARIANT(32, 16), STG_VARIANT(48, 24),
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr size_t kSmemCap = 200 * 1024;
@@ -917,6 +919,7 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
   const int M = Mmax;
   if (M > 256) { snprintf(err, errlen, "w*N=%d nodes per graph > 256 unsupported", M); return -2; }
   p.CP = v->CP; p.HP = v->HP;
+  p.mma_f = 0; p.mma_b = 0; p.NT = 0;
   const int slot = (M * (M + 1) > M * v->HP ? M * (M + 1) : M * v->HP);
   int wpc = 256 / M; if (wpc < 1) wpc = 1;
   // ---- forward: windows per chunk == windows in flight unless shared memory says otherwise
@@ -937,6 +940,8 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
       break;
     }
   }
+  // tensor-core forward when the graph fits the instantiated tiles (overrides the SIMT chunking)
+  if (!getenv("STG_NO_MMA")) plan_blocks_mma_fwd(a, p);
   // ---- backward: time steps per chunk so that the touching windows fit one pass
   for (int wp = wpc; wp >= 1; --wp) {
     int rows_max = 0, gx = 0;
@@ -961,6 +966,8 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
       break;
     }
   }
+  // tensor-core backward is opt-in (STG_MMA_BWD=1): at 1 CTA/SM it does not beat the SIMT kernel yet
+  if (!getenv("STG_NO_MMA") && getenv("STG_MMA_BWD")) plan_blocks_mma_bwd(a, p);
   return 0;
 }
 
@@ -1012,7 +1019,9 @@ int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
       ProfScope ps(kProfBlkPrep, s);
       k_block_prep<<<a.nblk, 256, 0, s>>>(a, p.CP, p.HP);
     }
-    {
+    if (p.mma_f) {
+      launch_block_forward_mma(a, p, s);
+    } else {
       ProfScope ps(kProfFwdMain, s);
       v->fwd_train<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max, p.wpc_f, slot);
     }
@@ -1023,6 +1032,8 @@ int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
     }
     ProfScope ps(kProfFwdFin, s);
     k_block_fwd_fin<<<dim3((unsigned)((tot + 255) / 256), 1, a.nblk), 256, 0, s>>>(a);
+  } else if (p.mma_f) {
+    launch_block_forward_mma(a, p, s);
   } else {
     ProfScope ps(kProfFwdMain, s);
     v->fwd_eval<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max, p.wpc_f, slot);
@@ -1049,7 +1060,9 @@ int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
     ProfScope ps(kProfBwdStats, s);
     v->bwd_stats<<<dim3(g, 1, a.nblk), 256, 0, s>>>(a);
   }
-  {
+  if (p.mma_b) {
+    launch_block_backward_mma(a, p, s);
+  } else {
     ProfScope ps(kProfBwdMain, s);
     v->bwd<<<dim3(p.grid_x_b, a.B, a.nblk), p.threads_b, p.smem_b, s>>>(a, rows_max, p.wpc_b, slot);
   }

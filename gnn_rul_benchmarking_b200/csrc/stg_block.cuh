@@ -36,6 +36,8 @@ struct BlkArgs {
 
 struct BlkPlan {
   int CP, HP;           // padded feature dims the kernel template is instantiated for
+  int mma_f, mma_b;     // tensor-core path selected for forward / backward
+  int NT;               // tensor-core path: 8-column tiles per graph (w*N <= 8*NT)
   int threads_f, threads_b;
   int wpc_f, wpc_b;     // windows processed concurrently per CTA
   size_t smem_f, smem_b;
@@ -45,6 +47,12 @@ struct BlkPlan {
 // Fills nchunk_* of every block and the launch plan; returns 0 or a negative stg_status
 // (message in err).  Pure host arithmetic.
 int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen);
+
+// tensor-core path (stg_block_mma.cu)
+bool plan_blocks_mma_fwd(BlkArgs& a, BlkPlan& p);
+bool plan_blocks_mma_bwd(BlkArgs& a, BlkPlan& p);
+int launch_block_forward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
+int launch_block_backward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
 
 // Launchers (enqueue only).
 int launch_xmoments(const float* x, int B, int T, int N, int C, double* xmom, cudaStream_t s);
