@@ -200,6 +200,8 @@ def run_native(args):
     alg.train()
     if world > 1:
         alg.attach_data_parallel()      # one NCCL all-reduce of the flat gradient buffer per step
+    if not args.no_graph:
+        alg.enable_cuda_graph(B)        # the step's launches replayed from one CUDA graph
 
     g = torch.Generator().manual_seed(1234 + rank)
     nbuf = 4
@@ -246,6 +248,7 @@ def run_native(args):
         ms_res = timed(step_resident, args.steps)
         ms_e2e = timed(step_e2e, args.steps)
     # second pass: same steps with per-kernel events of our library (roofline of the dominant kernel)
+    alg.disable_cuda_graph()            # event pairs cannot be recorded inside a graph replay
     with _lib.kernel_profile() as prof:
         timed(step_resident, args.steps)
     kern = prof.result()
@@ -284,6 +287,7 @@ def run_native(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][1]}", "global_batch": world * B,
                    "per_gpu_batch": B, "step": "fwd+mse+bwd+adam", "parallelism": f"dp{world}",
+                   "cuda_graph": not args.no_graph,
                    "l2": "flushed between steps (256 MiB memset outside the event pairs)"},
         "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
@@ -305,6 +309,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="windows per GPU per step")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

@@ -63,7 +63,7 @@ class StgModelParams(C.Structure):
 
 
 class StgDropout(C.Structure):
-    _fields_ = [("keep", C.c_void_p), ("seed", C.c_uint64)]
+    _fields_ = [("keep", C.c_void_p), ("seed", C.c_uint64), ("step_dev", C.c_void_p)]
 
 
 MODEL_SIGNATURES = {

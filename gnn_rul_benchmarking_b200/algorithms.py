@@ -55,9 +55,60 @@ class FC_STGNN(Algorithm):
                     dist.broadcast(t, 0, group=group)
         self.optimizer.grad_scale = 1.0 / self._dp_world
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the step
+    def enable_cuda_graph(self, batch_size):
+        """Captures one optimisation step (all library launches + the gradient exchange) for windows of
+        `batch_size` into a CUDA graph; later step()/update() calls with that batch size copy X, y into
+        static buffers and replay it.  Model/optimizer state is saved before the warm-up and capture
+        and restored afterwards, so enabling the graph does not change training."""
+        eng = self.model.engine
+        fl = eng.flatten()
+        dev = fl["param"].device
+        _, st = self.optimizer._state()
+        m = self.model
+        N, L = m.MPNN1.num_sensors, m.num_patch * m.patch_size
+        self._gX = torch.zeros(batch_size, N, L, device=dev)
+        self._gy = torch.zeros(batch_size, 1, device=dev)
+        eng.graph_seed = (int(torch.randint(0, 2 ** 62, (1,)).item()), torch.zeros(1, dtype=torch.int64, device=dev))
+        snap = [t.clone() for t in (fl["param"], st["exp_avg"], st["exp_avg_sq"], st["step"])]
+        bufs = [b for b in m.buffers()]
+        snap_b = [b.clone() for b in bufs]
+        was_training = self.training
+        self.train()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._eager_step(self._gX, self._gy)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._gloss = self._eager_step(self._gX, self._gy)
+        with torch.no_grad():
+            for t, s0 in zip((fl["param"], st["exp_avg"], st["exp_avg_sq"], st["step"]), snap):
+                t.copy_(s0)
+            for b, s0 in zip(bufs, snap_b):
+                b.copy_(s0)
+            eng.graph_seed[1].zero_()
+        self.train(was_training)
+        self._graph, self._graph_bs = graph, batch_size
+
+    def disable_cuda_graph(self):
+        self._graph = None
+        self.model.engine.graph_seed = None
+
     def step(self, X, y):
         """One optimisation step (forward -> MSE -> backward -> [all-reduce] -> Adam) with everything
         left on the device; returns the loss as a 0-dim device tensor."""
+        g = getattr(self, "_graph", None)
+        if g is not None and X.shape[0] == self._graph_bs and self.training:
+            self._gX.copy_(X, non_blocking=True)
+            self._gy.copy_(y.reshape(self._gy.shape), non_blocking=True)
+            g.replay()
+            return self._gloss
+        return self._eager_step(X, y)
+
+    def _eager_step(self, X, y):
         eng = self.model.engine
         loss = eng.loss_backward(X, y, zero_grad=True)
         if self._dp_world > 1:

@@ -1025,13 +1025,15 @@ int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
       ProfScope ps(kProfFwdMain, s);
       v->fwd_train<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max, p.wpc_f, slot);
     }
-    long long tot = 0;
-    for (int z = 0; z < a.nblk; ++z) {
-      const long long t = (long long)a.B * a.b[z].L * a.N * a.b[z].H;
-      tot = t > tot ? t : tot;
+    if (!a.head_fused) {
+      long long tot = 0;
+      for (int z = 0; z < a.nblk; ++z) {
+        const long long t = (long long)a.B * a.b[z].L * a.N * a.b[z].H;
+        tot = t > tot ? t : tot;
+      }
+      ProfScope ps(kProfFwdFin, s);
+      k_block_fwd_fin<<<dim3((unsigned)((tot + 255) / 256), 1, a.nblk), 256, 0, s>>>(a);
     }
-    ProfScope ps(kProfFwdFin, s);
-    k_block_fwd_fin<<<dim3((unsigned)((tot + 255) / 256), 1, a.nblk), 256, 0, s>>>(a);
   } else if (p.mma_f) {
     launch_block_forward_mma(a, p, s);
   } else {
@@ -1047,8 +1049,12 @@ int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   const int M = a.b[0].w * a.N;
   const int slot = (M * (M + 1) > M * p.HP ? M * (M + 1) : M * p.HP);
   const int rows_max = rows_max_bwd(a);
-  for (int z = 0; z < a.nblk; ++z)
-    cudaMemsetAsync(a.b[z].stats + 2 * a.b[z].H, 0, sizeof(double) * (2 * a.b[z].H + 2 * a.C), s);
+  for (int z = 0; z < a.nblk; ++z) {
+    if (a.head_fused)      // [2H,4H) was filled by k_head_bwd1 (zeroed by the forward's memset)
+      cudaMemsetAsync(a.b[z].stats + 4 * a.b[z].H, 0, sizeof(double) * (2 * a.C), s);
+    else
+      cudaMemsetAsync(a.b[z].stats + 2 * a.b[z].H, 0, sizeof(double) * (2 * a.b[z].H + 2 * a.C), s);
+  }
   long long rows = 0;
   for (int z = 0; z < a.nblk; ++z) {
     const long long r = (long long)a.B * a.b[z].L * M;
@@ -1056,7 +1062,7 @@ int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   }
   int g = (int)((rows + 255) / 256);
   if (g > 592) g = 592;
-  {
+  if (!a.head_fused) {
     ProfScope ps(kProfBwdStats, s);
     v->bwd_stats<<<dim3(g, 1, a.nblk), 256, 0, s>>>(a);
   }

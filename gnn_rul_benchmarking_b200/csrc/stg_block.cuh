@@ -32,6 +32,9 @@ struct BlkArgs {
   float* dx;            // backward finalize output
   int training;
   float momentum, eps;
+  // whole-model engine: the FC-head kernels take over BN1+leaky_relu+pool (k_block_fwd_fin) and the
+  // BN1 backward sums (k_block_bwd_stats), see stg_head.cu
+  int head_fused;
 };
 
 struct BlkPlan {

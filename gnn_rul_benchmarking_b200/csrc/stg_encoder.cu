@@ -61,7 +61,8 @@ STG_DEVINL float keep_scale(const EncArgs& a, size_t idx) {
   if (!a.training || a.pdrop <= 0.f) return 1.f;
   const float sc = 1.f / (1.f - a.pdrop);
   if (a.keep) return a.keep[idx] * sc;
-  unsigned long long z = a.seed + (unsigned long long)idx * 0x9E3779B97F4A7C15ull;
+  unsigned long long z = a.seed + (a.seed_ptr ? (unsigned long long)*a.seed_ptr * 0xD1B54A32D192ED03ull : 0ull) +
+                         (unsigned long long)idx * 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z ^= z >> 31;

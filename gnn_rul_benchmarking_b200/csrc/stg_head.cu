@@ -13,19 +13,71 @@ namespace stg {
 namespace {
 
 // ------------------------------------------------------------------------------------------
-template <int JP, int SPB>
-__global__ void __launch_bounds__(256) k_head_fc1(const HeadArgs a) {
+// BN1 coefficients of the graph-conv blocks from their batch moments: c[z][0]=a1 [1]=c1 [2]=mu1 [3]=r1
+STG_DEVINL void head_bn1(const HeadArgs& a, float (*c)[4][64], bool update_running) {
+  for (int i = threadIdx.x; i < a.nblk * 64; i += blockDim.x) {
+    const int z = i >> 6, h = i & 63;
+    const HeadBlk& k = a.blk[z];
+    if (h >= k.H) continue;
+    const double R = (double)a.B * k.L * k.M;
+    const double m = k.stats[h] / R;
+    double var = k.stats[k.H + h] / R - m * m;
+    if (var < 0.0) var = 0.0;
+    const float r1 = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float a1 = k.g1[h] * r1;
+    c[z][0][h] = a1;
+    c[z][1][h] = k.b1[h] - a1 * (float)m;
+    c[z][2][h] = (float)m;
+    c[z][3][h] = r1;
+    if (update_running) {
+      const double unb = R > 1.0 ? var * R / (R - 1.0) : var;
+      k.rm1[h] = (1.f - a.momentum) * k.rm1[h] + a.momentum * (float)m;
+      k.rv1[h] = (1.f - a.momentum) * k.rv1[h] + a.momentum * (float)unb;
+    }
+  }
+}
+
+// z1[b][j] += sum_{k in slice} feat[b][k] W1[j][k]  (+ b1[j] from slice 0).  grid (ceil(B/SPB), KSPLIT).
+// FUSED: feat[b][k] = mean_j lrelu(BN1(Y'[b,l,j*N+n,h])) is computed here from the blocks' saved Y'
+// (GraphConvpoolMPNN_block_v6 tail, Model_Base.py:103-107,212-216) and written to feat_out.
+template <int JP, int SPB, bool FUSED>
+__global__ void __launch_bounds__(256) k_head_fc1(const HeadArgs a, int kper) {
   __shared__ float red[8][SPB * JP];
+  __shared__ float bc[2][4][64];
   const int b0 = blockIdx.x * SPB, tid = threadIdx.x, J = a.J, F = a.F;
+  const int k_lo = blockIdx.y * kper, k_hi = min(F, k_lo + kper);
+  if (FUSED) {
+    head_bn1(a, bc, blockIdx.x == 0 && blockIdx.y == 0);
+    __syncthreads();
+  }
   float acc[SPB][JP];
 #pragma unroll
   for (int s = 0; s < SPB; ++s)
 #pragma unroll
     for (int j = 0; j < JP; ++j) acc[s][j] = 0.f;
-  for (int k = tid; k < F; k += 256) {
+  for (int k = k_lo + tid; k < k_hi; k += 256) {
     float f[SPB];
+    if (FUSED) {
+      const int z = (a.nblk > 1 && k >= a.blk[1].foff) ? 1 : 0;
+      const HeadBlk& kb = a.blk[z];
+      const int e = k - kb.foff, h = e % kb.H, ln = e / kb.H, n = ln % kb.N, l = ln / kb.N;
+      const float a1 = bc[z][0][h], c1 = bc[z][1][h], invw = 1.f / (float)kb.w;
+      const size_t jst = (size_t)kb.N * kb.H;
 #pragma unroll
-    for (int s = 0; s < SPB; ++s) f[s] = (b0 + s < a.B) ? a.feat[(size_t)(b0 + s) * F + k] : 0.f;
+      for (int s = 0; s < SPB; ++s) {
+        float v = 0.f;
+        if (b0 + s < a.B) {
+          const float* yp = kb.yp + (((size_t)(b0 + s) * kb.L + l) * kb.M + n) * kb.H + h;
+          for (int j = 0; j < kb.w; ++j) v += lrelu(fmaf(a1, yp[j * jst], c1));
+          v *= invw;
+          a.feat_out[(size_t)(b0 + s) * F + k] = v;
+        }
+        f[s] = v;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < SPB; ++s) f[s] = (b0 + s < a.B) ? a.feat[(size_t)(b0 + s) * F + k] : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < JP; ++j)
       if (j < J) {
@@ -46,10 +98,10 @@ __global__ void __launch_bounds__(256) k_head_fc1(const HeadArgs a) {
   if (tid < SPB * JP) {
     const int s = tid / JP, j = tid - s * JP;
     if (j < J && b0 + s < a.B) {
-      float v = a.b1[j];
+      float v = blockIdx.y == 0 ? a.b1[j] : 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) v += red[w][tid];
-      a.z1[(size_t)(b0 + s) * J + j] = v;
+      atomicAdd(&a.z1[(size_t)(b0 + s) * J + j], v);
     }
   }
 }
@@ -180,37 +232,88 @@ static size_t tail_smem(int J, int H, int TB) {
 
 // ------------------------------------------------------------------------------------------
 // grid (ceil(F/128), BS); thread = one feature column k, samples [b_lo, b_hi) of slice blockIdx.y
-template <int JP>
+//   dfeat[b][k] = sum_j d1[b][j] W1[j][k];  dW1[j][k] += sum_b d1[b][j] feat[b][k]
+// FUSED: also the BatchNorm-1 backward sums of the graph-conv blocks (what k_block_bwd_stats computes):
+//   stats[2H+h] += sum dYn, stats[3H+h] += sum dYn*Yhat, with dYn = dfeat/w * lrelu'(BN1(Y')).
+template <int JP, bool FUSED>
 __global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
   extern __shared__ __align__(16) float sm[];   // d1 slice [bper][J]
+  __shared__ float bc[2][4][64];
+  __shared__ float sred[2][2][64];
   const int J = a.J, F = a.F, tid = threadIdx.x;
   const int b_lo = blockIdx.y * bper, b_hi = min(a.B, b_lo + bper);
   for (int i = tid; i < (b_hi - b_lo) * J; i += blockDim.x) sm[i] = a.d1[(size_t)b_lo * J + i];
+  if (FUSED) {
+    head_bn1(a, bc, false);
+    for (int i = tid; i < 2 * 2 * 64; i += blockDim.x) (&sred[0][0][0])[i] = 0.f;
+  }
   __syncthreads();
   const int k = blockIdx.x * blockDim.x + tid;
-  if (k >= F) return;
-  float wc[JP], gw[JP];
+  if (k < F) {
+    float wc[JP], gw[JP];
 #pragma unroll
-  for (int j = 0; j < JP; ++j) {
-    wc[j] = j < J ? a.W1[(size_t)j * F + k] : 0.f;
-    gw[j] = 0.f;
-  }
-  for (int b = b_lo; b < b_hi; ++b) {
-    const float f = a.feat[(size_t)b * F + k];
-    const float* d = sm + (b - b_lo) * J;
-    float df = 0.f;
+    for (int j = 0; j < JP; ++j) {
+      wc[j] = j < J ? a.W1[(size_t)j * F + k] : 0.f;
+      gw[j] = 0.f;
+    }
+    int z = 0, h = 0, w = 1;
+    size_t ybase = 0, jst = 0, bst = 0;
+    float a1 = 0.f, c1 = 0.f, mu = 0.f, r1 = 0.f, invw = 1.f, s1 = 0.f, s2 = 0.f;
+    const float* yp = nullptr;
+    if (FUSED) {
+      z = (a.nblk > 1 && k >= a.blk[1].foff) ? 1 : 0;
+      const HeadBlk& kb = a.blk[z];
+      const int e = k - kb.foff;
+      h = e % kb.H;
+      const int ln = e / kb.H, n = ln % kb.N, l = ln / kb.N;
+      w = kb.w; invw = 1.f / (float)w;
+      ybase = ((size_t)l * kb.M + n) * kb.H + h;
+      jst = (size_t)kb.N * kb.H;
+      bst = (size_t)kb.L * kb.M * kb.H;
+      yp = kb.yp;
+      a1 = bc[z][0][h]; c1 = bc[z][1][h]; mu = bc[z][2][h]; r1 = bc[z][3][h];
+    }
+    for (int b = b_lo; b < b_hi; ++b) {
+      const float f = a.feat[(size_t)b * F + k];
+      const float* d = sm + (b - b_lo) * J;
+      float df = 0.f;
+#pragma unroll
+      for (int j = 0; j < JP; ++j)
+        if (j < J) {
+          const float dj = d[j];
+          df = fmaf(dj, wc[j], df);
+          gw[j] = fmaf(dj, f, gw[j]);
+        }
+      a.dfeat[(size_t)b * F + k] = df;
+      if (FUSED) {
+        const float* y = yp + (size_t)b * bst + ybase;
+        for (int j = 0; j < w; ++j) {
+          const float yv = y[j * jst];
+          const float dyn = df * invw * (fmaf(a1, yv, c1) > 0.f ? 1.f : kLeaky);
+          s1 += dyn;
+          s2 = fmaf(dyn, (yv - mu) * r1, s2);
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < JP; ++j)
-      if (j < J) {
-        const float dj = d[j];
-        df = fmaf(dj, wc[j], df);
-        gw[j] = fmaf(dj, f, gw[j]);
-      }
-    a.dfeat[(size_t)b * F + k] = df;
+      if (j < J) atomicAdd(&a.dW1[(size_t)j * F + k], gw[j]);
+    if (FUSED) {
+      atomicAdd(&sred[z][0][h], s1);
+      atomicAdd(&sred[z][1][h], s2);
+    }
   }
-#pragma unroll
-  for (int j = 0; j < JP; ++j)
-    if (j < J) atomicAdd(&a.dW1[(size_t)j * F + k], gw[j]);
+  if (FUSED) {
+    __syncthreads();
+    for (int i = tid; i < a.nblk * 64; i += blockDim.x) {
+      const int z = i >> 6, h = i & 63;
+      const HeadBlk& kb = a.blk[z];
+      if (h < kb.H) {
+        atomicAdd(&kb.stats[2 * kb.H + h], (double)sred[z][0][h]);
+        atomicAdd(&kb.stats[3 * kb.H + h], (double)sred[z][1][h]);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -245,7 +348,15 @@ __global__ void __launch_bounds__(256) k_zero(float4* p, size_t n4) {
 
 template <int JP, int SPB>
 void fc1_launch(const HeadArgs& a, cudaStream_t s) {
-  k_head_fc1<JP, SPB><<<(a.B + SPB - 1) / SPB, 256, 0, s>>>(a);
+  const int gx = (a.B + SPB - 1) / SPB;
+  int ksplit = (2 * 148 + gx - 1) / gx;              // about two CTAs per SM
+  const int maxsplit = (a.F + 511) / 512;
+  if (ksplit > maxsplit) ksplit = maxsplit;
+  if (ksplit < 1) ksplit = 1;
+  const int kper = (((a.F + ksplit - 1) / ksplit) + 3) / 4 * 4;
+  ksplit = (a.F + kper - 1) / kper;
+  if (a.fused_blocks) k_head_fc1<JP, SPB, true><<<dim3(gx, ksplit), 256, 0, s>>>(a, kper);
+  else k_head_fc1<JP, SPB, false><<<dim3(gx, ksplit), 256, 0, s>>>(a, kper);
 }
 template <int JP>
 void bwd1_launch(const HeadArgs& a, cudaStream_t s) {
@@ -255,10 +366,11 @@ void bwd1_launch(const HeadArgs& a, cudaStream_t s) {
   int bper = (a.B + slices - 1) / slices;
   if ((size_t)bper * a.J * 4 > 40 * 1024) bper = (int)(40 * 1024 / (a.J * 4));
   slices = (a.B + bper - 1) / bper;
-  k_head_bwd1<JP><<<dim3(gx, slices), 128, (size_t)bper * a.J * 4, s>>>(a, bper);
+  if (a.fused_blocks) k_head_bwd1<JP, true><<<dim3(gx, slices), 128, (size_t)bper * a.J * 4, s>>>(a, bper);
+  else k_head_bwd1<JP, false><<<dim3(gx, slices), 128, (size_t)bper * a.J * 4, s>>>(a, bper);
 }
 
-int tail_tb(int J) { return J <= 32 ? 128 : 32; }
+int tail_tb(int J) { (void)J; return 32; }
 bool g_tail_attr[64] = {};
 void tail_attrs() {
   int dev = 0;

@@ -20,6 +20,7 @@ struct EncArgs {
   const float* pe;            // [>=T, C]
   const float* keep;          // optional [B*N, T, C] 0/1 mask
   unsigned long long seed;
+  const long long* seed_ptr;  // optional device-side step counter mixed into the seed (CUDA-graph replays)
   float pdrop;
   int training;
   float momentum, eps;
@@ -42,8 +43,24 @@ bool encoder_fast_available(const EncArgs& a);
 int launch_encoder_fast(const EncArgs& a, bool backward, cudaStream_t s);
 
 // ---- FC head (Model.py:30-39,83) + MSE -------------------------------------------------------
+// One graph-conv block as the head sees it (training): pre-BN Y' saved by k_block_fwd, its batch
+// moments, BN1 parameters.  Lets k_head_fc1 apply BN1 + leaky_relu + window mean on the fly (replaces
+// k_block_fwd_fin) and k_head_bwd1 accumulate the BN1 backward sums (replaces k_block_bwd_stats).
+struct HeadBlk {
+  const float* yp;            // [B, L, w*N, H]
+  double* stats;              // [0,H) sum Y'  [H,2H) sum Y'^2  [2H,3H) sum dYn  [3H,4H) sum dYn*Yhat
+  const float *g1, *b1;
+  float *rm1, *rv1;
+  int L, M, H, N, w;
+  int foff;                   // first feature column of this block
+};
 struct HeadArgs {
   int B, F, J, H;             // J = 2H
+  int fused_blocks;           // 1: features come from blk[].yp (training), 0: feat is already final
+  int nblk;
+  HeadBlk blk[2];
+  float momentum, eps;
+  float* feat_out;            // [B, F] written by k_head_fc1 when fused_blocks
   const float* feat;          // [B, F]
   const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4;
   float* z1;                  // [B, J] pre-activation of fc1 (workspace)

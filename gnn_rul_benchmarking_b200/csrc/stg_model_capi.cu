@@ -52,7 +52,6 @@ void layout(const stg_model_dims& d, const Geo& g, Ws& w) {
   w.dfeat = o; o += al((size_t)d.B * g.F * 4);
   for (int z = 0; z < 2; ++z) { w.yp[z] = o; o += al((size_t)d.B * g.L[z] * g.M[z] * d.H * 4); }
   for (int z = 0; z < 2; ++z) { w.dxp[z] = o; o += rc; }
-  w.z1 = o; o += al((size_t)d.B * g.J * 4);
   w.d1 = o; o += al((size_t)d.B * g.J * 4);
   {
     const size_t tiles = ((size_t)g.R + 255) / 256;
@@ -62,6 +61,7 @@ void layout(const stg_model_dims& d, const Geo& g, Ws& w) {
     w.dn1 = o; o += al(tiles * g.NL1 * 256 * 4);
   }
   w.dbl = o;                                                   // ---- zeroed at the start of every forward
+  w.z1 = o; o += al((size_t)d.B * g.J * 4);                    // fc1 accumulates split-K partial sums
   w.xmom = o; o += al((size_t)2 * d.T * g.C * 8);
   for (int z = 0; z < 2; ++z) { w.bst[z] = o; o += al((size_t)STG_BLOCK_STATS_DOUBLES(g.C, d.H, d.T) * 8); }
   w.est = o; o += al((size_t)enc_stats_doubles(d.EH, d.E, g.C) * 8);
@@ -111,6 +111,7 @@ int build_ctx(Ctx& c, const stg_model_dims* dp, const stg_model_params* pp, cons
     return set_err(STG_ERR_INVALID, "null encoder parameter pointer");
   e.keep = drop ? drop->keep : nullptr;
   e.seed = drop ? drop->seed : 0ull;
+  e.seed_ptr = drop ? (const long long*)drop->step_dev : nullptr;
   e.pdrop = d.pe_dropout;
   if (e.pdrop < 0.f || e.pdrop >= 1.f) return set_err(STG_ERR_INVALID, "pe_dropout must be in [0,1)");
   e.training = training; e.momentum = d.bn_momentum; e.eps = d.bn_eps;
@@ -133,6 +134,7 @@ int build_ctx(Ctx& c, const stg_model_dims* dp, const stg_model_params* pp, cons
   a.nblk = STG_MAX_BLOCKS; a.x = e.h; a.B = d.B; a.T = d.T; a.N = d.N; a.C = g.C;
   a.xmom = (const double*)(base + c.w.xmom);
   a.training = training; a.momentum = d.bn_momentum; a.eps = d.bn_eps;
+  a.head_fused = training ? 1 : 0;
   a.dx = (float*)(base + c.w.dh);
   size_t foff = 0;
   for (int z = 0; z < STG_MAX_BLOCKS; ++z) {
@@ -169,6 +171,20 @@ int build_ctx(Ctx& c, const stg_model_dims* dp, const stg_model_params* pp, cons
   memset(&hd, 0, sizeof(hd));
   hd.B = d.B; hd.F = g.F; hd.J = g.J; hd.H = d.H;
   hd.feat = (const float*)(base + c.w.feat);
+  hd.feat_out = (float*)(base + c.w.feat);
+  hd.fused_blocks = training ? 1 : 0;
+  hd.nblk = STG_MAX_BLOCKS;
+  hd.momentum = d.bn_momentum; hd.eps = d.bn_eps;
+  {
+    int foff2 = 0;
+    for (int z = 0; z < STG_MAX_BLOCKS; ++z) {
+      HeadBlk& hb = hd.blk[z];
+      const BlkDev& k = a.b[z];
+      hb.yp = k.yp; hb.stats = k.stats; hb.g1 = k.g1; hb.b1 = k.b1; hb.rm1 = k.rm1; hb.rv1 = k.rv1;
+      hb.L = g.L[z]; hb.M = g.M[z]; hb.H = d.H; hb.N = d.N; hb.w = d.w[z]; hb.foff = foff2;
+      foff2 += (int)g.fsz[z];
+    }
+  }
   hd.W1 = p.fc_w[0]; hd.b1 = p.fc_b[0]; hd.W2 = p.fc_w[1]; hd.b2 = p.fc_b[1];
   hd.W3 = p.fc_w[2]; hd.b3 = p.fc_b[2]; hd.W4 = p.fc_w[3]; hd.b4 = p.fc_b[3];
   for (int i = 0; i < 4; ++i)
@@ -190,13 +206,13 @@ int build_ctx(Ctx& c, const stg_model_dims* dp, const stg_model_params* pp, cons
 // encoder -> h, x-moments, both blocks -> feat, fc1 -> z1 [-> pred when with_tail]
 int run_forward(Ctx& c, const stg_model_params& p, int training, float* pred, bool with_tail, cudaStream_t s) {
   char* base = (char*)c.enc.h - c.w.h;
+  launch_zero(base + c.w.dbl, c.w.dbl_end - c.w.dbl, s);
   if (training) {
-    launch_zero(base + c.w.dbl, c.w.dbl_end - c.w.dbl, s);
-    long long* nbt[7] = {(long long*)p.bn1.num_batches_tracked, (long long*)p.bn2.num_batches_tracked,
+    long long* nbt[8] = {(long long*)p.bn1.num_batches_tracked, (long long*)p.bn2.num_batches_tracked,
                          (long long*)p.bn3.num_batches_tracked, (long long*)p.blk[0].bn0.num_batches_tracked,
                          (long long*)p.blk[0].bn1.num_batches_tracked, (long long*)p.blk[1].bn0.num_batches_tracked,
-                         (long long*)p.blk[1].bn1.num_batches_tracked};
-    launch_tick(nbt, 7, s);
+                         (long long*)p.blk[1].bn1.num_batches_tracked, (long long*)c.enc.seed_ptr};
+    launch_tick(nbt, 8, s);
   }
   launch_encoder_forward(c.enc, c.enc_smem_f, s);
   if (training) launch_xmoments(c.enc.h, c.blk.B, c.blk.T, c.blk.N, c.blk.C, (double*)(base + c.w.xmom), s);

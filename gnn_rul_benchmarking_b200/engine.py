@@ -88,6 +88,7 @@ class ModelEngine:
         self._ws: Dict[Tuple, torch.Tensor] = {}
         self._gen = 0              # bumped by every training forward (detects a clobbered workspace)
         self.flat: Optional[dict] = None
+        self.graph_seed = None     # (base seed, device step counter) while a CUDA graph drives the dropout
 
     # ---------------------------------------------------------------- binding
     def _tensors(self):
@@ -145,6 +146,9 @@ class ModelEngine:
         if keep is not None and d.pe_dropout > 0:
             keep = keep.to(device=X.device, dtype=torch.float32).contiguous()
             dr.keep = keep.data_ptr()
+        elif d.pe_dropout > 0 and self.graph_seed is not None:
+            dr.seed = self.graph_seed[0]                               # + device counter, ticked per step
+            dr.step_dev = self.graph_seed[1].data_ptr()
         elif d.pe_dropout > 0:
             dr.seed = int(torch.randint(0, 2 ** 62, (1,)).item())     # CPU generator: follows torch.manual_seed
         return dr, keep

@@ -178,8 +178,10 @@ typedef struct stg_model_params { /* device pointers, state_dict names in commen
  *   keep != NULL : 0/1 float mask laid out like the reference's dropout input [B*N, T, C]
  *                  (Model.py:64-65) -- used to pin the mask in parity tests;
  *   keep == NULL : counter-based generator keyed by (seed, element index); the same (seed) must be
- *                  passed to the backward call.  pe_dropout == 0 disables it. */
-typedef struct stg_dropout { const float* keep; uint64_t seed; } stg_dropout;
+ *                  passed to the backward call.  pe_dropout == 0 disables it.
+ *   step_dev     : optional device counter mixed into the seed; training forwards increment it on the
+ *                  device, so a captured CUDA graph draws a fresh mask on every replay. */
+typedef struct stg_dropout { const float* keep; uint64_t seed; int64_t* step_dev; } stg_dropout;
 
 /* Bytes of caller-provided device workspace for a batch of dims->B windows (activations saved for
  * backward + reduction scratch).  0 on invalid dims. */

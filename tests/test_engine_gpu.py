@@ -148,13 +148,14 @@ def test_eval_is_batch_independent_and_state_dict_roundtrip(tmp_path):
     with torch.no_grad():
         full = model(X)
         part = model(X[5:17].contiguous())
-    assert torch.equal(full[5:17], part)
+    # fc1 accumulates split-K partial sums with float atomics: equal up to summation order
+    assert float((full[5:17] - part).abs().max()) < 1e-6
     torch.save(model.state_dict(), tmp_path / "ck.pt")
     m2 = FC_STGNN_RUL(**cfg).to(dev)
     m2.load_state_dict(torch.load(tmp_path / "ck.pt"))
     m2.eval()
     with torch.no_grad():
-        assert torch.equal(m2(X), full)
+        assert float((m2(X) - full).abs().max()) < 1e-6
 
 
 def test_engine_errors():
@@ -174,3 +175,42 @@ def test_engine_errors():
     model(X)                                           # second training forward clobbers the workspace
     with pytest.raises(RuntimeError):
         p1.sum().backward()
+
+
+def test_cuda_graph_step_matches_eager_and_preserves_state():
+    """enable_cuda_graph() must not change training: state restored after capture, replayed steps
+    equal eager steps (dropout off), BatchNorm counters and the Adam step advance once per replay."""
+    from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
+    from gnn_rul_benchmarking_b200.configs import CONFIGS, TRAIN_PARAMS
+    dev = torch.device("cuda:0")
+    cfg = CONFIGS["FD004"]
+    gen = torch.Generator().manual_seed(21)
+    algs = []
+    for use_graph in (False, True):
+        torch.manual_seed(5)
+        alg = get_algorithm_class("FC_STGNN")(cfg, TRAIN_PARAMS, dev).to(dev)
+        alg.model.positional_encoding.dropout.p = 0.0
+        alg.train()
+        if use_graph:
+            alg.enable_cuda_graph(8)
+        algs.append(alg)
+    for it in range(3):
+        X, y = torch.rand(8, 14, 50, generator=gen).to(dev), torch.rand(8, 1, generator=gen).to(dev)
+        l0 = algs[0].update(X, y, it)["loss"]
+        l1 = algs[1].update(X, y, it)["loss"]
+        assert abs(l0 - l1) < 1e-5 * max(1.0, abs(l0)), it
+    sd0, sd1 = algs[0].model.state_dict(), algs[1].model.state_dict()
+    for k in sd0:
+        assert torch.allclose(sd0[k].float(), sd1[k].float(), atol=1e-5, rtol=1e-4), k
+    assert int(algs[1].model.MPNN2.BN.num_batches_tracked) == 3
+    assert int(algs[1].optimizer._st["step"]) == 3
+    # with dropout on, consecutive replays draw different masks
+    algs[1].disable_cuda_graph()
+    algs[1].model.positional_encoding.dropout.p = 0.1
+    algs[1].enable_cuda_graph(8)
+    X, y = torch.rand(8, 14, 50, generator=gen).to(dev), torch.rand(8, 1, generator=gen).to(dev)
+    sd = {k: v.clone() for k, v in algs[1].state_dict().items()}
+    la = algs[1].update(X, y, 0)["loss"]
+    algs[1].load_state_dict(sd)
+    lb = algs[1].update(X, y, 0)["loss"]
+    assert abs(la - lb) > 1e-7
