@@ -65,6 +65,13 @@ __global__ void __launch_bounds__(256) k_xmoments(const float* __restrict__ x, i
 // ------------------------------------------------------------------------------------------
 // shared-memory carve-up common to the forward / backward main kernels
 // ------------------------------------------------------------------------------------------
+// window scratch; in the backward kernel it is re-used for the [CPH][CP]+[CPH] parameter-gradient tile
+__host__ __device__ inline int sb_floats(int wpc, int slot, int CP, int CPH, bool bwd) {
+  int n = wpc * slot;
+  if (bwd && n < CPH * CP + CPH) n = CPH * CP + CPH;
+  return (n + 3) / 4 * 4;
+}
+
 template <int CP, int HP>
 struct Carve {
   static constexpr int CPH = CP + HP;
@@ -85,7 +92,7 @@ struct Carve {
     WcT = p; p += CP * CPH;
     xs = p; p += ((rows_max * C + 4 + 3) / 4) * 4 + 4;
     FV = p; p += rows_max * CPH;
-    Sb = p; p += wpc * slot;
+    Sb = p; p += sb_floats(wpc, slot, CP, CP + HP, bwd);
     if (bwd) {
       WmS = p; p += CP * CP;
       WtS = p; p += HP * CP;
@@ -100,7 +107,7 @@ struct Carve {
 static size_t carve_bytes(int CP, int HP, int rows_max, int C, int wpc, int slot, int M, bool bwd) {
   const int CPH = CP + HP;
   size_t f = 4 * CP + CPH + 8 * HP + 4 + (size_t)CP * CPH + (((size_t)rows_max * C + 4 + 3) / 4) * 4 + 4 +
-             (size_t)rows_max * CPH + (size_t)wpc * slot;
+             (size_t)rows_max * CPH + (size_t)sb_floats(wpc, slot, CP, CPH, bwd);
   if (bwd)
     f += (size_t)CP * CP + (size_t)HP * CP + (size_t)rows_max * CPH + (((size_t)wpc * M + 3) / 4) * 4 +
          (size_t)wpc * M * HP + 2 * CP + 2 * HP;
@@ -731,26 +738,48 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
     }
   __syncthreads();
 
-  // ---- owned rows: dx partial + BN0 backward sums
+  // ---- owned rows: dx partial + BN0 backward sums.  thread = (row slot, 4 feature columns):
+  //      [dF | dV] row (CPH values, broadcast reads) x [Wm ; Wtheta] columns (float4 reads)
   const int r_beg = (ta - t_lo) * N, r_end = (tb - t_lo) * N;
   {
-    const int c = tid % CP, rg = tid / CP, nrg = nt / CP;
-    float sb = 0.f, sg = 0.f;
-    if (rg < nrg && c < C) {
+    constexpr int NQ = CP / 4;
+    const int cq = tid % NQ, rsl = tid / NQ, nrs = nt / NQ, c0i = cq * 4;
+    float sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rsl < nrs && c0i < C) {
       float* dxp = k.dxp + ((size_t)b * T + ta) * N * C;
-      for (int r = r_beg + rg; r < r_end; r += nrg) {
+      for (int r = r_beg + rsl; r < r_end; r += nrs) {
         const float* d = sm.dFV + (size_t)r * CPH;
-        float pF = 0.f, dXb = 0.f;
-        for (int o = 0; o < C; ++o) pF = fmaf(d[o], sm.WmS[o * CP + c], pF);
+        float pf[4] = {0.f, 0.f, 0.f, 0.f}, dx4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int o = 0; o < C; ++o) {
+          const float dv = d[o];
+          const float4 w4 = *reinterpret_cast<const float4*>(sm.WmS + o * CP + c0i);
+          pf[0] = fmaf(dv, w4.x, pf[0]); pf[1] = fmaf(dv, w4.y, pf[1]);
+          pf[2] = fmaf(dv, w4.z, pf[2]); pf[3] = fmaf(dv, w4.w, pf[3]);
+        }
 #pragma unroll
-        for (int h = 0; h < HP; ++h) dXb = fmaf(d[CP + h], sm.WtS[h * CP + c], dXb);
-        const float xh = (xs[r * C + c] - sm.mu0[c]) * sm.r0[c];
-        sb += dXb;
-        sg = fmaf(dXb, xh, sg);
-        dxp[(size_t)(r - r_beg) * C + c] = fmaf(dXb, sm.a0[c], pF);
+        for (int h = 0; h < HP; ++h) {
+          const float dv = d[CP + h];
+          const float4 w4 = *reinterpret_cast<const float4*>(sm.WtS + h * CP + c0i);
+          dx4[0] = fmaf(dv, w4.x, dx4[0]); dx4[1] = fmaf(dv, w4.y, dx4[1]);
+          dx4[2] = fmaf(dv, w4.z, dx4[2]); dx4[3] = fmaf(dv, w4.w, dx4[3]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0i + u;
+          if (c < C) {
+            const float xh = (xs[r * C + c] - sm.mu0[c]) * sm.r0[c];
+            sb[u] += dx4[u];
+            sg[u] = fmaf(dx4[u], xh, sg[u]);
+            dxp[(size_t)(r - r_beg) * C + c] = fmaf(dx4[u], sm.a0[c], pf[u]);
+          }
+        }
       }
-      atomicAdd(&sm.red[c], sb);
-      atomicAdd(&sm.red[CP + c], sg);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c0i + u < C) {
+          atomicAdd(&sm.red[c0i + u], sb[u]);
+          atomicAdd(&sm.red[CP + c0i + u], sg[u]);
+        }
     }
   }
 #pragma unroll
@@ -759,21 +788,43 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
     if ((tid & 31) == 0 && h < H) atomicAdd(&sm.red[2 * CP + h], v);
   }
   // ---- parameter gradients: G[o][c] = sum_rows dFV[r][o]*x[r][c],  so[o] = sum_rows dFV[r][o]
-  for (int idx = tid; idx < CPH * C; idx += nt) {
-    const int o = idx / C, c = idx - o * C;
-    const bool isF = o < C, isV = (o >= CP && o - CP < H);
-    if (!isF && !isV) continue;
-    float g = 0.f, so = 0.f;
-    for (int r = r_beg; r < r_end; ++r) {
-      const float d = sm.dFV[(size_t)r * CPH + o];
-      g = fmaf(d, xs[r * C + c], g);
-      so += d;
+  //      work item = (o, 4 columns), rows sliced over the remaining threads; partial sums meet in
+  //      shared memory (the window scratch is free now), one global atomic per entry per CTA.
+  {
+    constexpr int NQ = CP / 4;
+    float* Gs = sm.Sb;                                  // [CPH][CP] + so[CPH]   (<= slot floats, checked by the planner)
+    for (int i = tid; i < CPH * CP + CPH; i += nt) Gs[i] = 0.f;
+    __syncthreads();
+    const int items = CPH * NQ;
+    const int nsl = nt >= items ? nt / items : 1;
+    for (int it = tid; it < items * nsl; it += nt) {
+      const int item = it % items, sl = it / items;
+      const int o = item / NQ, c0i = (item - o * NQ) * 4;
+      float g4[4] = {0.f, 0.f, 0.f, 0.f}, so = 0.f;
+      for (int r = r_beg + sl; r < r_end; r += nsl) {
+        const float dv = sm.dFV[(size_t)r * CPH + o];
+        const float2 xa = *reinterpret_cast<const float2*>(xs + r * C + c0i);
+        const float2 xb = *reinterpret_cast<const float2*>(xs + r * C + c0i + 2);
+        g4[0] = fmaf(dv, xa.x, g4[0]); g4[1] = fmaf(dv, xa.y, g4[1]);
+        g4[2] = fmaf(dv, xb.x, g4[2]); g4[3] = fmaf(dv, xb.y, g4[3]);
+        so += dv;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) atomicAdd(&Gs[o * CP + c0i + u], g4[u]);
+      if (c0i == 0) atomicAdd(&Gs[CPH * CP + o], so);
     }
-    if (isF) {
-      atomicAdd(&k.dWm[o * C + c], g);
-      if (c == 0) atomicAdd(&k.dbm[o], so);
-    } else {
-      atomicAdd(&k.dWt[(o - CP) * C + c], fmaf(sm.a0[c], g, sm.c0[c] * so));
+    __syncthreads();
+    for (int idx = tid; idx < CPH * C; idx += nt) {
+      const int o = idx / C, c = idx - o * C;
+      const bool isF = o < C, isV = (o >= CP && o - CP < H);
+      if (!isF && !isV) continue;
+      const float g = Gs[o * CP + c], so = Gs[CPH * CP + o];
+      if (isF) {
+        atomicAdd(&k.dWm[o * C + c], g);
+        if (c == 0) atomicAdd(&k.dbm[o], so);
+      } else {
+        atomicAdd(&k.dWt[(o - CP) * C + c], fmaf(sm.a0[c], g, sm.c0[c] * so));
+      }
     }
   }
   __syncthreads();
@@ -942,29 +993,36 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
   }
   // tensor-core forward when the graph fits the instantiated tiles (overrides the SIMT chunking)
   if (!getenv("STG_NO_MMA")) plan_blocks_mma_fwd(a, p);
-  // ---- backward: time steps per chunk so that the touching windows fit one pass
-  for (int wp = wpc; wp >= 1; --wp) {
-    int rows_max = 0, gx = 0;
-    for (int z = 0; z < a.nblk; ++z) {
-      BlkDev& k = a.b[z];
-      int per = wp * k.stride - (k.w - 1);
-      if (per < k.stride) per = k.stride;
-      per = (per / k.stride) * k.stride;
-      k.nchunk_b = (a.T + per - 1) / per;
-      int per2 = (a.T + k.nchunk_b - 1) / k.nchunk_b;
-      per2 = ((per2 + k.stride - 1) / k.stride) * k.stride;
-      // worst-case staged time range: owned steps plus halo windows on both sides
-      const int span = per2 + 2 * (k.w - 1) + k.stride;
-      const int rows = (span < a.T ? span : a.T) * a.N;
-      rows_max = rows > rows_max ? rows : rows_max;
-      gx = k.nchunk_b > gx ? k.nchunk_b : gx;
-    }
-    const size_t sm = carve_bytes(v->CP, v->HP, rows_max, a.C, wp, slot, M, true);
-    if (sm <= kSmemCap || wp == 1) {
-      if (sm > kSmemCap) { snprintf(err, errlen, "backward tile does not fit shared memory (%zu B)", sm); return -2; }
-      p.wpc_b = wp; p.smem_b = sm; p.grid_x_b = gx; p.threads_b = ((wp * M + 31) / 32) * 32;
-      break;
-    }
+  // ---- backward: time steps per chunk so that the touching windows fit one pass.  Two sweeps: first
+  //      look for the largest tile that still lets 3 CTAs share an SM (the kernel is latency bound,
+  //      resident warps matter more than tile size), then for anything that fits at all.  Blocks
+  //      with a larger stride get fewer steps per chunk so that they do not dictate the slab size.
+  {
+    bool done = false;
+    const size_t caps[2] = {74 * 1024, kSmemCap};
+    for (int sweep = 0; sweep < 2 && !done; ++sweep)
+      for (int wp = wpc; wp >= 1 && !done; --wp) {
+        int gx = 0;
+        const int step_cap = wp + 1;                    // staged time steps of a stride-1, w=2 chunk
+        for (int z = 0; z < a.nblk; ++z) {
+          BlkDev& k = a.b[z];
+          int per = wp * k.stride - (k.w - 1);
+          if (per > step_cap - (k.w - 1) && step_cap - (k.w - 1) >= k.stride) per = step_cap - (k.w - 1);
+          if (per < k.stride) per = k.stride;
+          per = (per / k.stride) * k.stride;
+          k.nchunk_b = (a.T + per - 1) / per;
+          gx = k.nchunk_b > gx ? k.nchunk_b : gx;
+        }
+        int wmax = 0;
+        const int rows_max = bwd_rows_exact(a, &wmax);
+        if (wmax > wp) continue;                        // a chunk would touch more windows than slots
+        const size_t sm = carve_bytes(v->CP, v->HP, rows_max, a.C, wp, slot, M, true);
+        if (sm <= caps[sweep]) {
+          p.wpc_b = wp; p.smem_b = sm; p.grid_x_b = gx; p.threads_b = ((wp * M + 31) / 32) * 32;
+          done = true;
+        }
+      }
+    if (!done) { snprintf(err, errlen, "backward tile does not fit shared memory"); return -2; }
   }
   // tensor-core backward is opt-in (STG_MMA_BWD=1): at 1 CTA/SM it does not beat the SIMT kernel yet
   if (!getenv("STG_NO_MMA") && getenv("STG_MMA_BWD")) plan_blocks_mma_bwd(a, p);
@@ -981,18 +1039,7 @@ static int rows_max_fwd(const BlkArgs& a) {
   }
   return rm;
 }
-static int rows_max_bwd(const BlkArgs& a) {
-  int rm = 0;
-  for (int z = 0; z < a.nblk; ++z) {
-    const BlkDev& k = a.b[z];
-    int per2 = (a.T + k.nchunk_b - 1) / k.nchunk_b;
-    per2 = ((per2 + k.stride - 1) / k.stride) * k.stride;
-    const int span = per2 + 2 * (k.w - 1) + k.stride;
-    const int rows = (span < a.T ? span : a.T) * a.N;
-    rm = rows > rm ? rows : rm;
-  }
-  return rm;
-}
+static int rows_max_bwd(const BlkArgs& a) { return bwd_rows_exact(a); }
 
 int launch_xmoments(const float* x, int B, int T, int N, int C, double* xmom, cudaStream_t s) {
   cudaMemsetAsync(xmom, 0, sizeof(double) * 2 * T * C, s);

@@ -51,6 +51,34 @@ struct BlkPlan {
 // (message in err).  Pure host arithmetic.
 int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen);
 
+// Exact maximum of the rows a backward CTA stages (owned time steps plus the halo of the windows
+// touching them) over all chunks of all blocks, with the kernels' own chunk arithmetic; also
+// returns the largest number of windows a chunk touches.
+inline int bwd_rows_exact(const BlkArgs& a, int* max_windows = nullptr) {
+  int rm = 0, wm = 0;
+  for (int z = 0; z < a.nblk; ++z) {
+    const BlkDev& k = a.b[z];
+    const int w = k.w, s = k.stride, L = (a.T - w) / s + 1;
+    int per = (a.T + k.nchunk_b - 1) / k.nchunk_b;
+    per = ((per + s - 1) / s) * s;
+    for (int chunk = 0; chunk < k.nchunk_b; ++chunk) {
+      const int ta = chunk * per, tb = (a.T < ta + per) ? a.T : ta + per;
+      if (ta >= tb) continue;
+      int l_lo = ta - (w - 1);
+      l_lo = l_lo <= 0 ? 0 : (l_lo + s - 1) / s;
+      const int l_hi = (L - 1 < (tb - 1) / s) ? L - 1 : (tb - 1) / s;
+      const bool any = l_lo <= l_hi;
+      const int t_lo = any ? (ta < l_lo * s ? ta : l_lo * s) : ta;
+      const int t_hi = any ? (tb - 1 > l_hi * s + w - 1 ? tb - 1 : l_hi * s + w - 1) : tb - 1;
+      const int rows = (t_hi - t_lo + 1) * a.N;
+      rm = rows > rm ? rows : rm;
+      if (any && l_hi - l_lo + 1 > wm) wm = l_hi - l_lo + 1;
+    }
+  }
+  if (max_windows) *max_windows = wm;
+  return rm;
+}
+
 // tensor-core path (stg_block_mma.cu)
 bool plan_blocks_mma_fwd(BlkArgs& a, BlkPlan& p);
 bool plan_blocks_mma_bwd(BlkArgs& a, BlkPlan& p);

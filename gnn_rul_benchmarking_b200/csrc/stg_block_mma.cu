@@ -935,29 +935,7 @@ int rows_of_fwd(const BlkArgs& a) {
   }
   return rm;
 }
-// exact maximum of the staged rows over the backward chunks (same arithmetic as the kernel)
-int rows_of_bwd(const BlkArgs& a) {
-  int rm = 0;
-  for (int z = 0; z < a.nblk; ++z) {
-    const BlkDev& k = a.b[z];
-    const int w = k.w, s = k.stride, L = (a.T - w) / s + 1;
-    int per = (a.T + k.nchunk_b - 1) / k.nchunk_b;
-    per = ((per + s - 1) / s) * s;
-    for (int chunk = 0; chunk < k.nchunk_b; ++chunk) {
-      const int ta = chunk * per, tb = (a.T < ta + per) ? a.T : ta + per;
-      if (ta >= tb) continue;
-      int l_lo = ta - (w - 1);
-      l_lo = l_lo <= 0 ? 0 : (l_lo + s - 1) / s;
-      const int l_hi = (L - 1 < (tb - 1) / s) ? L - 1 : (tb - 1) / s;
-      const bool any = l_lo <= l_hi;
-      const int t_lo = any ? (ta < l_lo * s ? ta : l_lo * s) : ta;
-      const int t_hi = any ? (tb - 1 > l_hi * s + w - 1 ? tb - 1 : l_hi * s + w - 1) : tb - 1;
-      const int rows = (t_hi - t_lo + 1) * a.N;
-      rm = rows > rm ? rows : rm;
-    }
-  }
-  return rm;
-}
+int rows_of_bwd(const BlkArgs& a) { return bwd_rows_exact(a); }
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   if (!e) return dflt;

@@ -26,6 +26,8 @@ static int fill_args(BlkArgs& a, const float* x, int B, int T, int N, int C, con
                      float eps) {
   if (!x || !blk) return set_err(STG_ERR_INVALID, "null x / block descriptor");
   if (B < 1 || T < 1 || N < 1 || C < 1) return set_err(STG_ERR_INVALID, "non-positive dimension");
+  if (C & 1) return set_err(STG_ERR_UNSUPPORTED, "input_dim C=%d must be even (the reference uses C = 2*hidden_dim)", C);
+  if (((uintptr_t)x & 15) != 0) return set_err(STG_ERR_INVALID, "x must be 16-byte aligned");
   if (nblk < 1 || nblk > STG_MAX_BLOCKS) return set_err(STG_ERR_INVALID, "nblk must be 1..%d", STG_MAX_BLOCKS);
   if (training && !xmom) return set_err(STG_ERR_INVALID, "training mode needs xmom (stg_block_xmoments)");
   memset(&a, 0, sizeof(a));

@@ -127,6 +127,35 @@ STG_DEVINL void pair_reduce_f(float* accW, Fn f) {
   }
 }
 
+// one row of C contiguous floats (row pitch C): widest aligned vector access (C is even; rows are
+// 16-byte aligned when C % 4 == 0, 8-byte aligned otherwise)
+template <int C>
+STG_DEVINL void load_row(const float* __restrict__ p, float (&v)[C]) {
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(p + c);
+      v[c] = q.x; v[c + 1] = q.y; v[c + 2] = q.z; v[c + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; c += 2) {
+      const float2 q = *reinterpret_cast<const float2*>(p + c);
+      v[c] = q.x; v[c + 1] = q.y;
+    }
+  }
+}
+template <int C>
+STG_DEVINL void store_row(float* __restrict__ p, const float (&v)[C]) {
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < C; c += 4) *reinterpret_cast<float4*>(p + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; c += 2) *reinterpret_cast<float2*>(p + c) = make_float2(v[c], v[c + 1]);
+  }
+}
+
 STG_DEVINL float dot4(const float4 a, const float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 STG_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -163,18 +192,18 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
   if (PH >= 1) bn_coefs_f(cf1, EH, tr ? S1 : nullptr, cnt1, a.g1, a.be1, a.rm1, a.rv1, a.eps, a.momentum, tr && first && PH == 1);
   if (PH >= 2) bn_coefs_f(cf2, E, tr ? S2 : nullptr, cnt2, a.g2, a.be2, a.rm2, a.rv2, a.eps, a.momentum, tr && first && PH == 2);
   if (PH >= 3) bn_coefs_f(cf3, C, tr ? S3 : nullptr, cnt3, a.g3, a.be3, a.rm3, a.rv3, a.eps, a.momentum, tr && first && PH == 3);
-  if (PH == 3) for (int i = tid; i < T * C; i += kT) stage[i] = a.pe[i];
-  if (PH >= 5) for (int c = tid; c < C; c += kT) {
+  if (PH == 3 || PH == 8) for (int i = tid; i < T * C; i += kT) stage[i] = a.pe[i];
+  if (PH >= 5 && PH <= 7) for (int c = tid; c < C; c += kT) {
     q3[c] = (float)(Bq3[c] / cnt3);
     q3[C + c] = (float)(Bq3[C + c] / cnt3);
     if (PH == 5 && first) { a.dbe3[c] += (float)Bq3[c]; a.dg3[c] += (float)Bq3[C + c]; }
   }
-  if (PH >= 6) for (int c = tid; c < E; c += kT) {
+  if (PH >= 6 && PH <= 7) for (int c = tid; c < E; c += kT) {
     q2[c] = (float)(Bq2[c] / cnt2);
     q2[E + c] = (float)(Bq2[E + c] / cnt2);
     if (PH == 6 && first) { a.dbe2[c] += (float)Bq2[c]; a.dg2[c] += (float)Bq2[E + c]; }
   }
-  if (PH >= 7) for (int c = tid; c < EH; c += kT) {
+  if (PH == 7) for (int c = tid; c < EH; c += kT) {
     q1[c] = (float)(Bq1[c] / cnt1);
     q1[EH + c] = (float)(Bq1[EH + c] / cnt1);
     if (first) { a.dbe1[c] += (float)Bq1[c]; a.dg1[c] += (float)Bq1[EH + c]; }
@@ -205,16 +234,16 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
 
     // ---- x and conv1 where the phase needs them ----
     float x[P], c1[NL1];
-    constexpr bool NEED_C1 = PH == 0 || PH == 1 || PH == 6 || PH == 7;
-    if (NEED_C1 || PH == 3) {
+    constexpr bool NEED_C1 = PH == 0 || PH == 1 || PH == 6 || PH == 7 || PH == 8;
+    if (NEED_C1) {
 #pragma unroll
       for (int i = 0; i < P; ++i) x[i] = 0.f;
-      if (act && (NEED_C1 || !tr)) {
+      if (act) {
         const float* xp = a.X + ((size_t)(b * N + n) * T + t) * P;
 #pragma unroll
         for (int i = 0; i < P; ++i) x[i] = xp[i];
       }
-      if (NEED_C1 || !tr) conv1_row<D>(W1, x, c1);
+      conv1_row<D>(W1, x, c1);
     }
 
     if constexpr (PH == 0) {
@@ -249,11 +278,11 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
         stat_add_f(sacc, e, s);
         stat_add_f(sacc, E + e, ss);
       }
-    } else if constexpr (PH == 2 || PH == 3) {
+    } else if constexpr (PH == 2 || PH == 3 || PH == 8) {
       float z[C];
-      if (PH == 2 || !tr) {
+      if constexpr (PH == 2 || PH == 8) {
         float a2[EL2];
-        if (PH == 2) {
+        if constexpr (PH == 2) {
 #pragma unroll
           for (int k = 0; k < EL2; ++k) a2[k] = fmaxf(fmaf(A2[k / L2], c2t[k * kT], C2[k / L2]), 0.f);
         } else {                 // eval forward: whole chain in one pass (no stored intermediates)
@@ -287,16 +316,20 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
         float* hr = a.h + (size_t)r * C;
         const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
         const float* pe = stage + t * C;
+        float hv[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) hr[c] = (fmaf(A3[c], z[c], C3[c]) + pe[c]) * keep_scale_f(a, kbase + c);
+        for (int c = 0; c < C; ++c) hv[c] = (fmaf(A3[c], z[c], C3[c]) + pe[c]) * keep_scale_f(a, kbase + c);
+        store_row<C>(hr, hv);
       }
     } else if constexpr (PH == 4) {
       const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
+      float dhv[C];
+      if (act) load_row<C>(a.dh + (size_t)r * C, dhv);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         float dhn = 0.f, zh = 0.f;
         if (act) {
-          dhn = a.dh[(size_t)r * C + c] * keep_scale_f(a, kbase + c);
+          dhn = dhv[c] * keep_scale_f(a, kbase + c);
           zh = (z3t[c * kT] - mu3[c]) * r3[c];
         }
         stat_add_f(sacc, c, dhn);
@@ -305,24 +338,22 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
     } else if constexpr (PH == 5) {
       float* sdz = stage;                 // [C][kTP]
       float* sa2 = stage + C * kTP;       // [EL2][kTP]
-      float dz[C], a2[EL2], c2[EL2];
+      float dz[C];
       const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
+      {
+        float dhv[C];
+        if (act) load_row<C>(a.dh + (size_t)r * C, dhv);
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float v = 0.f;
-        if (act) {
-          const float dhn = a.dh[(size_t)r * C + c] * keep_scale_f(a, kbase + c);
-          const float zh = (z3t[c * kT] - mu3[c]) * r3[c];
-          v = A3[c] * (dhn - q3[c] - zh * q3[C + c]);
+        for (int c = 0; c < C; ++c) {
+          float v = 0.f;
+          if (act) {
+            const float dhn = dhv[c] * keep_scale_f(a, kbase + c);
+            const float zh = (z3t[c * kT] - mu3[c]) * r3[c];
+            v = A3[c] * (dhn - q3[c] - zh * q3[C + c]);
+          }
+          dz[c] = v;
+          sdz[c * kTP + tid] = v;
         }
-        dz[c] = v;
-        sdz[c * kTP + tid] = v;
-      }
-#pragma unroll
-      for (int k = 0; k < EL2; ++k) {
-        c2[k] = act ? c2t[k * kT] : 0.f;
-        a2[k] = act ? fmaxf(fmaf(A2[k / L2], c2[k], C2[k / L2]), 0.f) : 0.f;
-        sa2[k * kTP + tid] = a2[k];
       }
 #pragma unroll
       for (int e = 0; e < E; ++e) {
@@ -330,14 +361,17 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
 #pragma unroll
         for (int p = 0; p < L2; ++p) {
           const int k = e * L2 + p;
+          const float c2v = act ? c2t[k * kT] : 0.f;
+          const float a2v = act ? fmaxf(fmaf(A2[e], c2v, C2[e]), 0.f) : 0.f;
+          sa2[k * kTP + tid] = a2v;
           float v = 0.f;
-          if (a2[k] > 0.f) {
+          if (a2v > 0.f) {
 #pragma unroll
             for (int c = 0; c < C; ++c) v = fmaf(dz[c], W3[c * EL2 + k], v);
           }
           dn2t[k * kT] = v;
           s += v;
-          sh = fmaf(v, (c2[k] - mu2[e]) * r2[e], sh);
+          sh = fmaf(v, (c2v - mu2[e]) * r2[e], sh);
         }
         stat_add_f(sacc, e, s);
         stat_add_f(sacc, E + e, sh);
@@ -355,7 +389,7 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
     } else if constexpr (PH == 6) {
       float* sdc = stage;                 // [EL2][kTP]
       float* sa1 = stage + EL2 * kTP;     // [NL1][kTP]
-      float dc2[EL2], a1[NL1];
+      float dc2[EL2];
 #pragma unroll
       for (int k = 0; k < EL2; ++k) {
         const int e = k / L2;
@@ -368,17 +402,14 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
         sdc[k * kTP + tid] = v;
       }
 #pragma unroll
-      for (int i = 0; i < NL1; ++i) {
-        a1[i] = act ? fmaxf(fmaf(A1[i / L1], c1[i], C1[i / L1]), 0.f) : 0.f;
-        sa1[i * kTP + tid] = a1[i];
-      }
-#pragma unroll
       for (int ch = 0; ch < EH; ++ch) {
         float s = 0.f, sh = 0.f;
 #pragma unroll
         for (int q = 0; q < L1; ++q) {
+          const float a1v = act ? fmaxf(fmaf(A1[ch], c1[ch * L1 + q], C1[ch]), 0.f) : 0.f;
+          sa1[(ch * L1 + q) * kTP + tid] = a1v;
           float v = 0.f;
-          if (a1[ch * L1 + q] > 0.f) {
+          if (a1v > 0.f) {
 #pragma unroll
             for (int e = 0; e < E; ++e)
 #pragma unroll
@@ -454,14 +485,15 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
 template <class D, int PH>
 size_t stage_bytes(int T) {
   size_t fl = 0;
-  if (PH == 3) fl = (size_t)T * D::C;
+  if (PH == 3 || PH == 8) fl = (size_t)T * D::C;
   if (PH == 5) fl = (size_t)(D::C + D::EL2) * kTP;
   if (PH == 6) fl = (size_t)(D::EL2 + D::NL1) * kTP;
   if (PH == 7) fl = (size_t)(D::NL1 + D::P) * kTP;
   return fl * 4;
 }
 
-const int kProfOfF[8] = {kProfEncF1, kProfEncF2, kProfEncF3, kProfEncF4, kProfEncB1, kProfEncB2, kProfEncB3, kProfEncB4};
+const int kProfOfF[9] = {kProfEncF1, kProfEncF2, kProfEncF3, kProfEncF4, kProfEncB1, kProfEncB2, kProfEncB3, kProfEncB4,
+                         kProfEncF4};
 
 int sms_f() {
   static int v = 0;
@@ -483,7 +515,7 @@ void launch_one(const EncArgs& a, cudaStream_t s) {
     attr_done = true;
   }
   const int ntiles = (a.R + kT - 1) / kT;
-  int per_sm = smem > 48 * 1024 ? 2 : smem > 24 * 1024 ? 3 : 4;
+  int per_sm = smem > 56 * 1024 ? 2 : smem > 40 * 1024 ? 4 : 6;
   int grid = sms_f() * per_sm;
   if (grid > ntiles) grid = ntiles;
   ProfScope ps(kProfOfF[PH], s);
@@ -503,8 +535,10 @@ void run(const EncArgs& a, bool backward, cudaStream_t s) {
       launch_one<D, 0>(a, s);
       launch_one<D, 1>(a, s);
       launch_one<D, 2>(a, s);
+      launch_one<D, 3>(a, s);
+    } else {
+      launch_one<D, 8>(a, s);           // eval: whole chain in one pass from running statistics
     }
-    launch_one<D, 3>(a, s);
   } else {
     launch_one<D, 4>(a, s);
     launch_one<D, 5>(a, s);

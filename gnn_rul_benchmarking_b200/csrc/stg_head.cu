@@ -236,7 +236,7 @@ static size_t tail_smem(int J, int H, int TB) {
 // FUSED: also the BatchNorm-1 backward sums of the graph-conv blocks (what k_block_bwd_stats computes):
 //   stats[2H+h] += sum dYn, stats[3H+h] += sum dYn*Yhat, with dYn = dfeat/w * lrelu'(BN1(Y')).
 template <int JP, bool FUSED>
-__global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
+__global__ void __launch_bounds__(128, 5) k_head_bwd1(const HeadArgs a, int bper) {
   extern __shared__ __align__(16) float sm[];   // d1 slice [bper][J]
   __shared__ float bc[2][4][64];
   __shared__ float sred[2][2][64];
@@ -389,7 +389,7 @@ int launch_head_forward(const HeadArgs& a, cudaStream_t s) {
   if (a.J > 64 || a.H > 64) return -2;
   {
     ProfScope ps(kProfHeadFc1, s);
-    if (a.J <= 16) fc1_launch<16, 4>(a, s);
+    if (a.J <= 16) fc1_launch<16, 2>(a, s);
     else if (a.J <= 32) fc1_launch<32, 2>(a, s);
     else if (a.J <= 48) fc1_launch<48, 1>(a, s);
     else fc1_launch<64, 1>(a, s);

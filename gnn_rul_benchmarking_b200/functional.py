@@ -154,4 +154,7 @@ def graph_blocks(x: torch.Tensor, hyper: Sequence[dict], tensors: Sequence[Seque
     hyper[k] = dict(H=, w=, stride=, decay=); tensors[k] = the 12 tensors in BLOCK_TENSORS order
     (running statistics are updated in place when training)."""
     flat = [t for blk in tensors for t in blk]
-    return _GraphBlocks.apply(x.contiguous(), tuple(dict(h) for h in hyper), bool(training), *flat)
+    x = x.contiguous()
+    if x.data_ptr() % 16:                       # a contiguous view at an odd offset: the kernels want 16-B alignment
+        x = x.clone()
+    return _GraphBlocks.apply(x, tuple(dict(h) for h in hyper), bool(training), *flat)
