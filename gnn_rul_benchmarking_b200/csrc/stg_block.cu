@@ -122,10 +122,9 @@ static size_t carve_bytes(int CP, int HP, int rows_max, int C, int wpc, int slot
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline int coef_floats(int CP, int HP, int T) { return 4 * CP + (CP + HP) + 4 + CP * (CP + HP) + T; }
 
-__global__ void __launch_bounds__(256) k_block_prep(const BlkArgs a, int CP, int HP) {
-  __shared__ double ssum[48], ssq[48];
-  __shared__ float sa0[48], sc0[48];
-  const BlkDev& k = a.b[blockIdx.x];
+STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const double* xmom, double* ssum,
+                                double* ssq, float* sa0, float* sc0) {
+  const BlkDev& k = a.b[z];
   const int C = a.C, T = a.T, H = k.H, tid = threadIdx.x, CPH = CP + HP;
   float* tab = k.coef;
   float* mu0 = tab; float* r0 = mu0 + CP; float* a0 = r0 + CP; float* c0 = a0 + CP;
@@ -140,8 +139,8 @@ __global__ void __launch_bounds__(256) k_block_prep(const BlkArgs a, int CP, int
       for (int t = sl; t < T; t += nsl) {
         const int cn = cover_count(t, k.w, k.stride, k.L);
         if (cn) {
-          s += cn * a.xmom[t * C + c];
-          q += cn * a.xmom[(size_t)T * C + t * C + c];
+          s += cn * __ldcg(xmom + t * C + c);            // written by other CTAs' atomics: read at L2
+          q += cn * __ldcg(xmom + (size_t)T * C + t * C + c);
         }
       }
       atomicAdd(&ssum[c], s);
@@ -188,6 +187,56 @@ __global__ void __launch_bounds__(256) k_block_prep(const BlkArgs a, int CP, int
       for (int c = 0; c < C; ++c) v += wr[c] * sc0[c];
     }
     biasc[o] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_block_prep(const BlkArgs a, int CP, int HP) {
+  __shared__ double ssum[48], ssq[48];
+  __shared__ float sa0[48], sc0[48];
+  block_prep_body(a, blockIdx.x, CP, HP, a.xmom, ssum, ssq, sa0, sc0);
+}
+
+// x-moments and, in the last CTA to finish, the coefficient tables of every block: one launch
+// instead of two on the critical path of the training forward.  grid (T, BCH); block 256.
+__global__ void __launch_bounds__(256) k_xmoments_prep(const BlkArgs a, int CP, int HP, double* xmom,
+                                                       unsigned* counter) {
+  __shared__ float sm[2 * 48];
+  __shared__ double ssum[48], ssq[48];
+  __shared__ float sa0[48], sc0[48];
+  __shared__ int s_last;
+  const int B = a.B, T = a.T, N = a.N, C = a.C;
+  const int t = blockIdx.x, nb = gridDim.y;
+  const int bper = (B + nb - 1) / nb;
+  const int b0 = blockIdx.y * bper, b1 = min(B, b0 + bper);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int NC = N * C;
+  for (int e = threadIdx.x; e < NC; e += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+    for (int b = b0; b < b1; ++b) {
+      const float v = a.x[((size_t)b * T + t) * NC + e];
+      s1 += v;
+      s2 = fmaf(v, v, s2);
+    }
+    const int c = e % C;
+    atomicAdd(&sm[c], s1);
+    atomicAdd(&sm[C + c], s2);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&xmom[t * C + c], (double)sm[c]);
+    atomicAdd(&xmom[(size_t)T * C + t * C + c], (double)sm[C + c]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int z = 0; z < a.nblk; ++z) {
+    block_prep_body(a, z, CP, HP, xmom, ssum, ssq, sa0, sc0);
+    __syncthreads();
   }
 }
 
@@ -1052,6 +1101,15 @@ int launch_xmoments(const float* x, int B, int T, int N, int C, double* xmom, cu
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
+// model path: x-moments + coefficient tables in one launch (xmom and counter must be zero on entry)
+int launch_xmoments_prep(const BlkArgs& a, const BlkPlan& p, double* xmom, unsigned* counter, cudaStream_t s) {
+  int nb = (a.B + 15) / 16;
+  if (nb > 64) nb = 64;
+  ProfScope ps(kProfXmoments, s);
+  k_xmoments_prep<<<dim3(a.T, nb), 256, 0, s>>>(a, p.CP, p.HP, xmom, counter);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
 int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   set_smem_attrs();
   const Variant* v = pick_variant(p.CP, p.HP);
@@ -1060,9 +1118,10 @@ int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   const int rows_max = rows_max_fwd(a);
   dim3 grid(p.grid_x_f, a.B, a.nblk);
   if (a.training) {
-    for (int z = 0; z < a.nblk; ++z)
-      cudaMemsetAsync(a.b[z].stats, 0, sizeof(double) * (4 * a.b[z].H + 2 * a.C), s);
-    {
+    if (!a.prep_done)      // model path: the step's first kernel already cleared the whole scratch region
+      for (int z = 0; z < a.nblk; ++z)
+        cudaMemsetAsync(a.b[z].stats, 0, sizeof(double) * (4 * a.b[z].H + 2 * a.C), s);
+    if (!a.prep_done) {
       ProfScope ps(kProfBlkPrep, s);
       k_block_prep<<<a.nblk, 256, 0, s>>>(a, p.CP, p.HP);
     }
@@ -1097,8 +1156,8 @@ int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   const int slot = (M * (M + 1) > M * p.HP ? M * (M + 1) : M * p.HP);
   const int rows_max = rows_max_bwd(a);
   for (int z = 0; z < a.nblk; ++z) {
-    if (a.head_fused)      // [2H,4H) was filled by k_head_bwd1 (zeroed by the forward's memset)
-      cudaMemsetAsync(a.b[z].stats + 4 * a.b[z].H, 0, sizeof(double) * (2 * a.C), s);
+    if (a.head_fused)      // model path: [2H,4H) was filled by k_head_bwd1, the rest is still zero from the
+      continue;            // forward's clear (one backward per training forward)
     else
       cudaMemsetAsync(a.b[z].stats + 2 * a.b[z].H, 0, sizeof(double) * (2 * a.b[z].H + 2 * a.C), s);
   }

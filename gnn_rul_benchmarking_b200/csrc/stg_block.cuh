@@ -35,6 +35,7 @@ struct BlkArgs {
   // whole-model engine: the FC-head kernels take over BN1+leaky_relu+pool (k_block_fwd_fin) and the
   // BN1 backward sums (k_block_bwd_stats), see stg_head.cu
   int head_fused;
+  int prep_done;        // coefficient tables already written by k_xmoments_prep
 };
 
 struct BlkPlan {
@@ -87,6 +88,7 @@ int launch_block_backward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s
 
 // Launchers (enqueue only).
 int launch_xmoments(const float* x, int B, int T, int N, int C, double* xmom, cudaStream_t s);
+int launch_xmoments_prep(const BlkArgs& a, const BlkPlan& p, double* xmom, unsigned* counter, cudaStream_t s);
 int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
 int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
 

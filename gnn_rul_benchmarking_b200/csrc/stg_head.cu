@@ -134,51 +134,65 @@ __global__ void __launch_bounds__(128) k_head_tail(const HeadArgs a, int TB) {
   if (tid == 0) bb[J + H] = a.b4[0];
   if (MODE) for (int i = tid; i < nacc; i += nt) acc[i] = 0.f;
   __syncthreads();
-  const int b = blockIdx.x * TB + tid;
-  const bool act = tid < TB && b < a.B;
+  // four threads per sample: each owns every 4th output of a layer; the sample's activations live in
+  // its shared-memory column, layers are separated by __syncwarp (the 4 threads share a warp)
+  const int sl = tid >> 2, part = tid & 3;          // sample slot in the tile, part of the sample
+  const int b = blockIdx.x * TB + sl;
+  const bool act = sl < TB && b < a.B;
   float pred = 0.f;
-  if (act) {
-    for (int j = 0; j < J; ++j) a1[j * TBP + tid] = fmaxf(a.z1[(size_t)b * J + j], 0.f);
-    for (int i = 0; i < J; ++i) {
+  if (act)
+    for (int j = part; j < J; j += 4) a1[j * TBP + sl] = fmaxf(a.z1[(size_t)b * J + j], 0.f);
+  __syncwarp();
+  if (act)
+    for (int i = part; i < J; i += 4) {
       float v = bb[i];
-      for (int j = 0; j < J; ++j) v = fmaf(W2[i * J + j], a1[j * TBP + tid], v);
-      a2[i * TBP + tid] = fmaxf(v, 0.f);
+      for (int j = 0; j < J; ++j) v = fmaf(W2[i * J + j], a1[j * TBP + sl], v);
+      a2[i * TBP + sl] = fmaxf(v, 0.f);
     }
-    for (int i = 0; i < H; ++i) {
+  __syncwarp();
+  if (act)
+    for (int i = part; i < H; i += 4) {
       float v = bb[J + i];
-      for (int j = 0; j < J; ++j) v = fmaf(W3[i * J + j], a2[j * TBP + tid], v);
-      a3[i * TBP + tid] = fmaxf(v, 0.f);
+      for (int j = 0; j < J; ++j) v = fmaf(W3[i * J + j], a2[j * TBP + sl], v);
+      a3[i * TBP + sl] = fmaxf(v, 0.f);
     }
-    pred = bb[J + H];
-    for (int i = 0; i < H; ++i) pred = fmaf(W4[i], a3[i * TBP + tid], pred);
-    if (a.pred) a.pred[b] = pred;
-  }
+  __syncwarp();
+  if (act)
+    for (int i = part; i < H; i += 4) pred = fmaf(W4[i], a3[i * TBP + sl], pred);
+  pred += __shfl_xor_sync(0xffffffffu, pred, 1);
+  pred += __shfl_xor_sync(0xffffffffu, pred, 2);
+  pred += bb[J + H];
+  if (act && part == 0 && a.pred) a.pred[b] = pred;
   if (MODE == 0) return;
   float dp = 0.f, lossv = 0.f;
   if (act) {
     if (MODE == 2) {
       const float e = pred - a.y[b];
-      lossv = e * e / (float)a.B;
+      lossv = part == 0 ? e * e / (float)a.B : 0.f;
       dp = 2.f * e / (float)a.B;
     } else {
       dp = a.dpred[b];
     }
-    for (int i = 0; i < H; ++i) dd3[i * TBP + tid] = a3[i * TBP + tid] > 0.f ? dp * W4[i] : 0.f;
-    for (int j = 0; j < J; ++j) {
+    for (int i = part; i < H; i += 4) dd3[i * TBP + sl] = a3[i * TBP + sl] > 0.f ? dp * W4[i] : 0.f;
+    if (part == 0) dps[sl] = dp;
+  }
+  __syncwarp();
+  if (act)
+    for (int j = part; j < J; j += 4) {
       float v = 0.f;
-      if (a2[j * TBP + tid] > 0.f)
-        for (int i = 0; i < H; ++i) v = fmaf(dd3[i * TBP + tid], W3[i * J + j], v);
-      dd2[j * TBP + tid] = v;
+      if (a2[j * TBP + sl] > 0.f)
+        for (int i = 0; i < H; ++i) v = fmaf(dd3[i * TBP + sl], W3[i * J + j], v);
+      dd2[j * TBP + sl] = v;
     }
-    for (int j = 0; j < J; ++j) {
+  __syncwarp();
+  if (act)
+    for (int j = part; j < J; j += 4) {
       float v = 0.f;
-      if (a1[j * TBP + tid] > 0.f)
-        for (int i = 0; i < J; ++i) v = fmaf(dd2[i * TBP + tid], W2[i * J + j], v);
-      dd1[j * TBP + tid] = v;
+      if (a1[j * TBP + sl] > 0.f)
+        for (int i = 0; i < J; ++i) v = fmaf(dd2[i * TBP + sl], W2[i * J + j], v);
+      dd1[j * TBP + sl] = v;
       a.d1[(size_t)b * J + j] = v;
     }
-    dps[tid] = dp;
-  }
   if (MODE == 2) {
     lossv = warp_sum(lossv);
     if ((tid & 31) == 0) atomicAdd(&acc[nacc - 1], lossv);
@@ -236,7 +250,7 @@ static size_t tail_smem(int J, int H, int TB) {
 // FUSED: also the BatchNorm-1 backward sums of the graph-conv blocks (what k_block_bwd_stats computes):
 //   stats[2H+h] += sum dYn, stats[3H+h] += sum dYn*Yhat, with dYn = dfeat/w * lrelu'(BN1(Y')).
 template <int JP, bool FUSED>
-__global__ void __launch_bounds__(128, 5) k_head_bwd1(const HeadArgs a, int bper) {
+__global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
   extern __shared__ __align__(16) float sm[];   // d1 slice [bper][J]
   __shared__ float bc[2][4][64];
   __shared__ float sred[2][2][64];
@@ -336,14 +350,20 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
   }
 }
 
-struct TickArgs { long long* p[16]; int n; };
+struct TickArgs { long long* p[16]; int n; float* zero1; };
 __global__ void k_tick(const TickArgs t) {
   if (threadIdx.x < t.n && t.p[threadIdx.x]) *t.p[threadIdx.x] += 1;
 }
 
-__global__ void __launch_bounds__(256) k_zero(float4* p, size_t n4) {
+// first kernel of a step: clears the reduction scratch, increments the step counters
+// (num_batches_tracked, dropout counter) and clears one extra word (the caller's loss accumulator)
+__global__ void __launch_bounds__(256) k_zero(float4* p, size_t n4, const TickArgs t) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
     p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < t.n && t.p[threadIdx.x]) *t.p[threadIdx.x] += 1;
+    if (threadIdx.x == 0 && t.zero1) *t.zero1 = 0.f;
+  }
 }
 
 template <int JP, int SPB>
@@ -420,14 +440,18 @@ int launch_head_backward(const HeadArgs& a, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
-int launch_zero(void* p, size_t bytes, cudaStream_t s) {
+int launch_zero(void* p, size_t bytes, long long* const* counters, int ncounters, float* zero1, cudaStream_t s) {
   // bytes must be a multiple of 16 and p 16-byte aligned (workspace segments are)
   const size_t n4 = bytes / 16;
-  if (!n4) return 0;
   int grid = (int)((n4 + 255) / 256);
   if (grid > 1184) grid = 1184;
+  if (grid < 1) grid = 1;
+  TickArgs t = {};
+  t.n = ncounters > 16 ? 16 : ncounters;
+  for (int i = 0; i < t.n; ++i) t.p[i] = counters[i];
+  t.zero1 = zero1;
   ProfScope ps(kProfZero, s);
-  k_zero<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(p), n4);
+  k_zero<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(p), n4, t);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

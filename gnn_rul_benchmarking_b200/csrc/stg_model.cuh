@@ -76,7 +76,7 @@ int launch_head_forward(const HeadArgs& a, cudaStream_t s);               // fea
 int launch_head_backward(const HeadArgs& a, cudaStream_t s);              // (y | dpred) -> grads, dfeat
 
 // ---- misc -------------------------------------------------------------------------------------
-int launch_zero(void* p, size_t bytes, cudaStream_t s);
+int launch_zero(void* p, size_t bytes, long long* const* counters, int ncounters, float* zero1, cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, long long* step, float lr, float b1,
                 float b2, float eps, float wd, float gscale, cudaStream_t s);
 int launch_tick(long long* const* counters, int n, cudaStream_t s);

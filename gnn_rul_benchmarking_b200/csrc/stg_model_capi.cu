@@ -11,7 +11,7 @@ namespace stg {
 namespace {
 
 struct Ws {            // byte offsets into the caller's workspace
-  size_t h, dh, feat, dfeat, yp[2], dxp[2], z1, d1, c2raw, z3raw, dn2, dn1, dbl, xmom, bst[2], est, loss, dbl_end,
+  size_t h, dh, feat, dfeat, yp[2], dxp[2], z1, d1, c2raw, z3raw, dn2, dn1, dbl, xmom, bst[2], est, loss, cnt, dbl_end,
       total;
 };
 struct Geo {
@@ -66,6 +66,7 @@ void layout(const stg_model_dims& d, const Geo& g, Ws& w) {
   for (int z = 0; z < 2; ++z) { w.bst[z] = o; o += al((size_t)STG_BLOCK_STATS_DOUBLES(g.C, d.H, d.T) * 8); }
   w.est = o; o += al((size_t)enc_stats_doubles(d.EH, d.E, g.C) * 8);
   w.loss = o; o += al(16);
+  w.cnt = o; o += al(16);
   w.dbl_end = o;
   w.total = o;
 }
@@ -204,18 +205,21 @@ int build_ctx(Ctx& c, const stg_model_dims* dp, const stg_model_params* pp, cons
 }
 
 // encoder -> h, x-moments, both blocks -> feat, fc1 -> z1 [-> pred when with_tail]
-int run_forward(Ctx& c, const stg_model_params& p, int training, float* pred, bool with_tail, cudaStream_t s) {
+int run_forward(Ctx& c, const stg_model_params& p, int training, float* pred, bool with_tail, float* zero1,
+                cudaStream_t s) {
   char* base = (char*)c.enc.h - c.w.h;
-  launch_zero(base + c.w.dbl, c.w.dbl_end - c.w.dbl, s);
-  if (training) {
-    long long* nbt[8] = {(long long*)p.bn1.num_batches_tracked, (long long*)p.bn2.num_batches_tracked,
-                         (long long*)p.bn3.num_batches_tracked, (long long*)p.blk[0].bn0.num_batches_tracked,
-                         (long long*)p.blk[0].bn1.num_batches_tracked, (long long*)p.blk[1].bn0.num_batches_tracked,
-                         (long long*)p.blk[1].bn1.num_batches_tracked, (long long*)c.enc.seed_ptr};
-    launch_tick(nbt, 8, s);
-  }
+  long long* nbt[8] = {(long long*)p.bn1.num_batches_tracked, (long long*)p.bn2.num_batches_tracked,
+                       (long long*)p.bn3.num_batches_tracked, (long long*)p.blk[0].bn0.num_batches_tracked,
+                       (long long*)p.blk[0].bn1.num_batches_tracked, (long long*)p.blk[1].bn0.num_batches_tracked,
+                       (long long*)p.blk[1].bn1.num_batches_tracked, (long long*)c.enc.seed_ptr};
+  // one launch: clear the reduction scratch, tick num_batches_tracked + dropout counter, clear the loss
+  launch_zero(base + c.w.dbl, c.w.dbl_end - c.w.dbl, nbt, training ? 8 : 0, zero1, s);
   launch_encoder_forward(c.enc, c.enc_smem_f, s);
-  if (training) launch_xmoments(c.enc.h, c.blk.B, c.blk.T, c.blk.N, c.blk.C, (double*)(base + c.w.xmom), s);
+  if (training) {
+    // block stats are cleared by the step's k_zero; tables come with the x-moments (one launch)
+    launch_xmoments_prep(c.blk, c.plan, (double*)(base + c.w.xmom), (unsigned*)(base + c.w.cnt), s);
+    c.blk.prep_done = 1;
+  }
   launch_block_forward(c.blk, c.plan, s);
   HeadArgs hd = c.head;
   hd.pred = with_tail ? pred : nullptr;
@@ -227,10 +231,7 @@ int run_forward(Ctx& c, const stg_model_params& p, int training, float* pred, bo
 int run_backward(Ctx& c, const float* y, const float* dpred, float* pred, cudaStream_t s) {
   HeadArgs hd = c.head;
   hd.y = y; hd.dpred = dpred; hd.pred = pred;
-  {  // backward halves of the encoder moments (forward zeroed them; keep repeated backwards correct)
-    const int fwd = 2 * (c.enc.EH + c.enc.E + c.enc.C);
-    cudaMemsetAsync(c.enc.st + fwd, 0, sizeof(double) * fwd, s);
-  }
+  // all backward sums were cleared by the forward's first kernel: ONE backward per training forward
   launch_head_backward(hd, s);
   launch_block_backward(c.blk, c.plan, s);
   launch_encoder_backward(c.enc, c.enc_smem_b, s);
@@ -260,7 +261,7 @@ int stg_model_forward(const stg_model_dims* dims, const stg_model_params* params
   Ctx c;
   int rc = build_ctx(c, dims, params, nullptr, X_dev, workspace, workspace_bytes, training, drop);
   if (rc) return rc;
-  return run_forward(c, *params, training, pred_dev, true, (cudaStream_t)stream);
+  return run_forward(c, *params, training, pred_dev, true, nullptr, (cudaStream_t)stream);
 }
 
 int stg_model_backward(const stg_model_dims* dims, const stg_model_params* params, const stg_model_params* grads,
@@ -283,8 +284,7 @@ int stg_model_loss_backward(const stg_model_dims* dims, const stg_model_params* 
   if (rc) return rc;
   c.head.loss = loss_dev;
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(loss_dev, 0, sizeof(float), s) != cudaSuccess) return check_cuda("memset loss");
-  rc = run_forward(c, *params, 1, nullptr, false, s);
+  rc = run_forward(c, *params, 1, nullptr, false, loss_dev, s);
   if (rc) return rc;
   return run_backward(c, y_dev, nullptr, pred_dev, s);
 }
