@@ -314,16 +314,17 @@ STG_DEVINL void compute_fv(const Carve<CP, HP>& sm, const float* xs, int rows, i
 
 template <int CP>
 STG_DEVINL float dot_cp(const float (&a)[CP], const float* __restrict__ b) {
-  float s = 0.f;
+  // four independent accumulators: the kernel is latency bound, a single fmaf chain of CP links is not
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int c = 0; c < CP; c += 4) {
     const float4 v = *reinterpret_cast<const float4*>(b + c);
-    s = fmaf(a[c], v.x, s);
-    s = fmaf(a[c + 1], v.y, s);
-    s = fmaf(a[c + 2], v.z, s);
-    s = fmaf(a[c + 3], v.w, s);
+    s0 = fmaf(a[c], v.x, s0);
+    s1 = fmaf(a[c + 1], v.y, s1);
+    s2 = fmaf(a[c + 2], v.z, s2);
+    s3 = fmaf(a[c + 3], v.w, s3);
   }
-  return s;
+  return (s0 + s1) + (s2 + s3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(256) k_block_fwd(const BlkArgs a, int rows_max
       }
       float* Srow = Sb + i * (M + 1);
       float mx = -INFINITY;
+#pragma unroll 2
       for (int kk = 0; kk < M; ++kk) {
         const float sv = lrelu(dot_cp<CP>(Fi, FVw + kk * CPH));
         Srow[kk] = sv;
@@ -691,6 +693,7 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
           Fi[c] = v.x; Fi[c + 1] = v.y; Fi[c + 2] = v.z; Fi[c + 3] = v.w;
         }
         float mx = -INFINITY;
+#pragma unroll 2
         for (int kk = 0; kk < M; ++kk) {
           const float sv = lrelu(dot_cp<CP>(Fi, FVw + kk * CPH));
           Srow[kk] = sv;
@@ -706,9 +709,13 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
             const float e = __expf(sv - mx);
             sum += e;
             const float* Vk = FVw + kk * CPH + CP;
-            float dA = 0.f;
+            float dA0 = 0.f, dA1 = 0.f;
 #pragma unroll
-            for (int h = 0; h < HP; ++h) dA = fmaf(dY[h], Vk[h], dA);
+            for (int h = 0; h < HP; h += 2) {
+              dA0 = fmaf(dY[h], Vk[h], dA0);
+              dA1 = fmaf(dY[h + 1], Vk[h + 1], dA1);
+            }
+            const float dA = dA0 + dA1;
             rs = fmaf(e * mk, dA, rs);
             Srow[kk] = sv > 0.f ? e : -e;
           }
@@ -747,9 +754,13 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
             const float ev = Srow[kk];
             const float P = fabsf(ev) * inv;
             const float* Vk = FVw + kk * CPH + CP;
-            float dA = 0.f;
+            float dA0 = 0.f, dA1 = 0.f;
 #pragma unroll
-            for (int h = 0; h < HP; ++h) dA = fmaf(dY[h], Vk[h], dA);
+            for (int h = 0; h < HP; h += 2) {
+              dA0 = fmaf(dY[h], Vk[h], dA0);
+              dA1 = fmaf(dY[h + 1], Vk[h + 1], dA1);
+            }
+            const float dA = dA0 + dA1;
             const float dLam = P * (dA * mk - rs);
             Srow[kk] = dLam * (ev > 0.f ? 1.f : kLeaky);
           }
@@ -823,9 +834,26 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
           }
         }
       }
+    }
+    // reduce over the row slots of each warp first (lanes NQ apart share the columns), then one
+    // shared atomic per warp and column -- not one per thread
+    if (NQ <= 32 && (32 % NQ) == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v1 = sb[u], v2 = sg[u];
+        for (int o = NQ; o < 32; o <<= 1) {
+          v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        }
+        if ((tid & 31) < NQ && c0i + u < C) {
+          atomicAdd(&sm.red[c0i + u], v1);
+          atomicAdd(&sm.red[CP + c0i + u], v2);
+        }
+      }
+    } else {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (c0i + u < C) {
+        if (rsl < nrs && c0i + u < C) {
           atomicAdd(&sm.red[c0i + u], sb[u]);
           atomicAdd(&sm.red[CP + c0i + u], sg[u]);
         }
@@ -841,11 +869,16 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
   //      shared memory (the window scratch is free now), one global atomic per entry per CTA.
   {
     constexpr int NQ = CP / 4;
-    float* Gs = sm.Sb;                                  // [CPH][CP] + so[CPH]   (<= slot floats, checked by the planner)
-    for (int i = tid; i < CPH * CP + CPH; i += nt) Gs[i] = 0.f;
-    __syncthreads();
+    // Gs[slice][CPH][CP] + so[slice][CPH]: every (item, slice) has one owner thread -> plain stores
+    float* Gs = sm.Sb;
+    constexpr int GSZ = CPH * CP + CPH;
     const int items = CPH * NQ;
-    const int nsl = nt >= items ? nt / items : 1;
+    int nsl = nt >= items ? nt / items : 1;
+    {
+      const int fit = sb_floats(wpc, slot, CP, CPH, true) / GSZ;
+      if (nsl > fit) nsl = fit;
+      if (nsl > 8) nsl = 8;
+    }
     for (int it = tid; it < items * nsl; it += nt) {
       const int item = it % items, sl = it / items;
       const int o = item / NQ, c0i = (item - o * NQ) * 4;
@@ -858,16 +891,21 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
         g4[2] = fmaf(dv, xb.x, g4[2]); g4[3] = fmaf(dv, xb.y, g4[3]);
         so += dv;
       }
+      float* Gp = Gs + sl * GSZ;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) atomicAdd(&Gs[o * CP + c0i + u], g4[u]);
-      if (c0i == 0) atomicAdd(&Gs[CPH * CP + o], so);
+      for (int u = 0; u < 4; ++u) Gp[o * CP + c0i + u] = g4[u];
+      if (c0i == 0) Gp[CPH * CP + o] = so;
     }
     __syncthreads();
     for (int idx = tid; idx < CPH * C; idx += nt) {
       const int o = idx / C, c = idx - o * C;
       const bool isF = o < C, isV = (o >= CP && o - CP < H);
       if (!isF && !isV) continue;
-      const float g = Gs[o * CP + c], so = Gs[CPH * CP + o];
+      float g = 0.f, so = 0.f;
+      for (int q = 0; q < nsl; ++q) {
+        g += Gs[q * GSZ + o * CP + c];
+        so += Gs[q * GSZ + CPH * CP + o];
+      }
       if (isF) {
         atomicAdd(&k.dWm[o * C + c], g);
         if (c == 0) atomicAdd(&k.dbm[o], so);
@@ -1048,7 +1086,9 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
   //      with a larger stride get fewer steps per chunk so that they do not dictate the slab size.
   {
     bool done = false;
-    const size_t caps[2] = {74 * 1024, kSmemCap};
+    size_t cap0 = 74 * 1024;
+    if (const char* e = getenv("STG_BWD_CAP_KB")) { const int v2 = atoi(e); if (v2 >= 16) cap0 = (size_t)v2 * 1024; }
+    const size_t caps[2] = {cap0, kSmemCap};
     for (int sweep = 0; sweep < 2 && !done; ++sweep)
       for (int wp = wpc; wp >= 1 && !done; --wp) {
         int gx = 0;

@@ -7,6 +7,7 @@
 //   F1 conv1 moments | F2 conv1,conv2 -> c2raw, moments | F3 c2raw -> linear -> z3raw, moments | F4 z3raw -> h
 //   B1 dh,z3raw -> BN3 sums | B2 -> dW3,db3, dn2, BN2 sums | B3 -> dW2, dn1, BN1 sums | B4 -> dW1
 #include <math.h>
+#include <stdlib.h>
 
 #include "stg_model.cuh"
 
@@ -62,9 +63,11 @@ STG_DEVINL void bn_coefs_f(float* dst, int n, const double* stats, double count,
   }
 }
 
-STG_DEVINL void stat_add_f(double* sacc, int idx, float v) {
+// per-warp partial sums in registers' place: swarp[warp][idx] accumulates this warp's tiles (one owner
+// lane per slot, no atomics); the CTA reduces the 8 warps in double at the very end
+STG_DEVINL void stat_add_f(float (*swarp)[2 * 48], int idx, float v) {
   v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[idx], (double)v);
+  if ((threadIdx.x & 31) == 0) swarp[threadIdx.x >> 5][idx] += v;
 }
 
 template <class D>
@@ -160,7 +163,7 @@ STG_DEVINL float dot4(const float4 a, const float4 b) { return a.x * b.x + a.y *
 STG_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 template <class D, int PH>
-__global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
+__global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs a) {
   constexpr int P = D::P, K = D::K, EH = D::EH, E = D::E, C = D::C, L1 = D::L1, L2 = D::L2, EL2 = D::EL2, NL1 = D::NL1;
   constexpr int MAXCH = EH > E ? (EH > C ? EH : C) : (E > C ? E : C);
   constexpr int NPAIR = PH == 5 ? C * EL2 + C : PH == 6 ? E * EH * K : PH == 7 ? EH * K : 1;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
   __shared__ float b3[C];
   __shared__ float cf1[4 * EH], cf2[4 * E], cf3[4 * C];
   __shared__ float q1[2 * EH], q2[2 * E], q3[2 * C];
-  __shared__ double sacc[2 * MAXCH];
+  __shared__ float sacc[kT / 32][2 * 48];
   __shared__ float accW[NPAIR];
   extern __shared__ __align__(16) float stage[];      // [features][kTP] columns for the pair reductions / pe
   const int tid = threadIdx.x;
@@ -209,7 +212,8 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
     if (first) { a.dbe1[c] += (float)Bq1[c]; a.dg1[c] += (float)Bq1[EH + c]; }
   }
   for (int i = tid; i < NPAIR; i += kT) accW[i] = 0.f;
-  for (int i = tid; i < 2 * MAXCH; i += kT) sacc[i] = 0.0;
+  static_assert(MAXCH <= 48, "stat slots");
+  for (int i = tid; i < (kT / 32) * 2 * 48; i += kT) (&sacc[0][0])[i] = 0.f;
   __syncthreads();
 
   const float *A1 = cf1, *C1 = cf1 + EH, *mu1 = cf1 + 2 * EH, *r1 = cf1 + 3 * EH;
@@ -218,6 +222,9 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
 
   const int ntiles = (a.R + kT - 1) / kT;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // compiler barrier: without it the weight loads (loop-invariant shared memory) are hoisted out of the
+    // tile loop into several hundred registers / local memory
+    asm volatile("" ::: "memory");
     const int r = tile * kT + tid;
     const bool act = r < a.R;
     int n = 0, t = 0, b = 0;
@@ -470,7 +477,12 @@ __global__ void __launch_bounds__(kT) k_enc_fast(const EncArgs a) {
   constexpr int nstat = PH == 0 ? EH : PH == 1 ? E : PH == 2 ? C : PH == 4 ? C : PH == 5 ? E : PH == 6 ? EH : 0;
   if (nstat) {
     double* dst = PH == 0 ? a.st : PH == 1 ? a.st + 2 * EH : PH == 2 ? a.st + 2 * (EH + E) : PH == 4 ? Bq3 : PH == 5 ? Bq2 : Bq1;
-    for (int i = tid; i < 2 * nstat; i += kT) atomicAdd(&dst[i], sacc[i]);
+    for (int i = tid; i < 2 * nstat; i += kT) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kT / 32; ++w) v += (double)sacc[w][i];
+      atomicAdd(&dst[i], v);
+    }
   }
   if (PH == 5) {
     for (int i = tid; i < C * EL2; i += kT) atomicAdd(&a.dW3[i], accW[i]);
@@ -516,6 +528,7 @@ void launch_one(const EncArgs& a, cudaStream_t s) {
   }
   const int ntiles = (a.R + kT - 1) / kT;
   int per_sm = smem > 56 * 1024 ? 2 : smem > 40 * 1024 ? 4 : 6;
+  if (const char* e = getenv("STG_ENC_PERSM")) { const int v = atoi(e); if (v >= 1) per_sm = v; }
   int grid = sms_f() * per_sm;
   if (grid > ntiles) grid = ntiles;
   ProfScope ps(kProfOfF[PH], s);

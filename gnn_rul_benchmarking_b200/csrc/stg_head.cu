@@ -317,6 +317,8 @@ __global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
       atomicAdd(&sred[z][1][h], s2);
     }
   }
+  // (the two shared atomics above are per thread; columns of one warp map to <= 32/H distinct (z,h)
+  //  pairs, contention stays below the global-load latency this kernel is bound by)
   if (FUSED) {
     __syncthreads();
     for (int i = tid; i < a.nblk * 64; i += blockDim.x) {
