@@ -123,13 +123,14 @@ static size_t carve_bytes(int CP, int HP, int rows_max, int C, int wpc, int slot
 __host__ __device__ inline int coef_floats(int CP, int HP, int T) { return 4 * CP + (CP + HP) + 4 + CP * (CP + HP) + T; }
 
 STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const double* xmom, double* ssum,
-                                double* ssq, float* sa0, float* sc0) {
+                                double* ssq, float* sa0, float* sc0, float* sWt) {
   const BlkDev& k = a.b[z];
   const int C = a.C, T = a.T, H = k.H, tid = threadIdx.x, CPH = CP + HP;
   float* tab = k.coef;
   float* mu0 = tab; float* r0 = mu0 + CP; float* a0 = r0 + CP; float* c0 = a0 + CP;
   float* biasc = c0 + CP; float* pw = biasc + CPH; float* WcT = pw + 4; float* cnt = WcT + CP * CPH;
   if (tid < 48) { ssum[tid] = 0.0; ssq[tid] = 0.0; }
+  for (int i = tid; i < H * C; i += 256) sWt[i] = k.Wt[i];      // staged: the bias loop below walks rows of it
   __syncthreads();
   // weighted moments of x over time: thread (c, slice of t)
   {
@@ -175,7 +176,7 @@ STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const d
     float v = 0.f;
     if (c < C) {
       if (o < C) v = k.Wm[o * C + c];
-      else if (o >= CP && o - CP < H) v = k.Wt[(o - CP) * C + c] * sa0[c];
+      else if (o >= CP && o - CP < H) v = sWt[(o - CP) * C + c] * sa0[c];
     }
     WcT[idx] = v;
   }
@@ -183,7 +184,7 @@ STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const d
     float v = 0.f;
     if (o < C) v = k.bm[o];
     else if (o >= CP && o - CP < H) {
-      const float* wr = k.Wt + (o - CP) * C;
+      const float* wr = sWt + (o - CP) * C;
       for (int c = 0; c < C; ++c) v += wr[c] * sc0[c];
     }
     biasc[o] = v;
@@ -192,8 +193,8 @@ STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const d
 
 __global__ void __launch_bounds__(256) k_block_prep(const BlkArgs a, int CP, int HP) {
   __shared__ double ssum[48], ssq[48];
-  __shared__ float sa0[48], sc0[48];
-  block_prep_body(a, blockIdx.x, CP, HP, a.xmom, ssum, ssq, sa0, sc0);
+  __shared__ float sa0[48], sc0[48], sWt[24 * 48];
+  block_prep_body(a, blockIdx.x, CP, HP, a.xmom, ssum, ssq, sa0, sc0, sWt);
 }
 
 // x-moments and, in the last CTA to finish, the coefficient tables of every block: one launch
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(256) k_xmoments_prep(const BlkArgs a, int CP, 
                                                        unsigned* counter) {
   __shared__ float sm[2 * 48];
   __shared__ double ssum[48], ssq[48];
-  __shared__ float sa0[48], sc0[48];
+  __shared__ float sa0[48], sc0[48], sWt[24 * 48];
   __shared__ int s_last;
   const int B = a.B, T = a.T, N = a.N, C = a.C;
   const int t = blockIdx.x, nb = gridDim.y;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(256) k_xmoments_prep(const BlkArgs a, int CP, 
   if (!s_last) return;
   __threadfence();
   for (int z = 0; z < a.nblk; ++z) {
-    block_prep_body(a, z, CP, HP, xmom, ssum, ssq, sa0, sc0);
+    block_prep_body(a, z, CP, HP, xmom, ssum, ssq, sa0, sc0, sWt);
     __syncthreads();
   }
 }
@@ -1218,6 +1219,7 @@ int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
     ProfScope ps(kProfBwdMain, s);
     v->bwd<<<dim3(p.grid_x_b, a.B, a.nblk), p.threads_b, p.smem_b, s>>>(a, rows_max, p.wpc_b, slot);
   }
+  if (a.fin_elsewhere) return cudaGetLastError() == cudaSuccess ? 0 : -3;
   const long long tot = (long long)a.B * a.T * a.N * a.C;
   ProfScope ps(kProfBwdFin, s);
   long long gfin = (tot / 4 + 255) / 256;

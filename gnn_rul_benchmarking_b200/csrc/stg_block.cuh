@@ -36,6 +36,7 @@ struct BlkArgs {
   // BN1 backward sums (k_block_bwd_stats), see stg_head.cu
   int head_fused;
   int prep_done;        // coefficient tables already written by k_xmoments_prep
+  int fin_elsewhere;    // k_block_bwd_fin's work is done by the encoder's first backward phase
 };
 
 struct BlkPlan {

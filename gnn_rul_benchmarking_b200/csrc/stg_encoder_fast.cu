@@ -211,6 +211,37 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
     q1[EH + c] = (float)(Bq1[EH + c] / cnt1);
     if (first) { a.dbe1[c] += (float)Bq1[c]; a.dg1[c] += (float)Bq1[EH + c]; }
   }
+  if (PH == 4 && a.fin.nblk) {
+    // stage: per block  mu0[C] r0[C] m1[C] m2[C] cnt[T]
+    for (int z = 0; z < a.fin.nblk; ++z) {
+      float* tb = stage + z * (4 * C + T);
+      const int Hz = a.fin.H[z];
+      const double Rz = (double)a.B * a.fin.L[z] * a.fin.w[z] * N;
+      for (int c = tid; c < C; c += kT) {
+        const float r0 = a.fin.tab[z][a.fin.CP + c];
+        const double sb = a.fin.stats[z][4 * Hz + c], sg = a.fin.stats[z][4 * Hz + C + c];
+        const float g0 = a.fin.g0[z][c];
+        tb[c] = a.fin.tab[z][c];
+        tb[C + c] = r0;
+        tb[2 * C + c] = r0 * (float)(g0 * sb / Rz);
+        tb[3 * C + c] = r0 * (float)(g0 * sg / Rz);
+        if (first) { a.fin.db0[z][c] += (float)sb; a.fin.dg0[z][c] += (float)sg; }
+      }
+      for (int t2 = tid; t2 < T; t2 += kT) {
+        int cn = 0;
+        for (int j = 0; j < a.fin.w[z]; ++j) {
+          const int d = t2 - j;
+          if (d >= 0 && d % a.fin.stride[z] == 0 && d / a.fin.stride[z] < a.fin.L[z]) ++cn;
+        }
+        tb[4 * C + t2] = (float)cn;
+      }
+      if (first)
+        for (int h = tid; h < Hz; h += kT) {
+          a.fin.db1[z][h] += (float)a.fin.stats[z][2 * Hz + h];
+          a.fin.dg1[z][h] += (float)a.fin.stats[z][3 * Hz + h];
+        }
+    }
+  }
   for (int i = tid; i < NPAIR; i += kT) accW[i] = 0.f;
   static_assert(MAXCH <= 48, "stat slots");
   for (int i = tid; i < (kT / 32) * 2 * 48; i += kT) (&sacc[0][0])[i] = 0.f;
@@ -331,7 +362,28 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
     } else if constexpr (PH == 4) {
       const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
       float dhv[C];
-      if (act) load_row<C>(a.dh + (size_t)r * C, dhv);
+      if (act) {
+        if (a.fin.nblk) {
+          float xv[C];
+          load_row<C>(a.h + (size_t)r * C, xv);
+#pragma unroll
+          for (int c = 0; c < C; ++c) dhv[c] = 0.f;
+          for (int z = 0; z < a.fin.nblk; ++z) {
+            const float* tb = stage + z * (4 * C + T);
+            const float cn = tb[4 * C + t];
+            float dv[C];
+            load_row<C>(a.fin.dxp[z] + (size_t)r * C, dv);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const float xh = (xv[c] - tb[c]) * tb[C + c];
+              dhv[c] += dv[c] - cn * (tb[2 * C + c] + xh * tb[3 * C + c]);
+            }
+          }
+          store_row<C>(a.fin.dh_out + (size_t)r * C, dhv);
+        } else {
+          load_row<C>(a.dh + (size_t)r * C, dhv);
+        }
+      }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         float dhn = 0.f, zh = 0.f;
@@ -498,6 +550,7 @@ template <class D, int PH>
 size_t stage_bytes(int T) {
   size_t fl = 0;
   if (PH == 3 || PH == 8) fl = (size_t)T * D::C;
+  if (PH == 4) fl = (size_t)2 * (4 * D::C + T);
   if (PH == 5) fl = (size_t)(D::C + D::EL2) * kTP;
   if (PH == 6) fl = (size_t)(D::EL2 + D::NL1) * kTP;
   if (PH == 7) fl = (size_t)(D::NL1 + D::P) * kTP;

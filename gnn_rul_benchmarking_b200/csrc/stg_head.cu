@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
       yp = kb.yp;
       a1 = bc[z][0][h]; c1 = bc[z][1][h]; mu = bc[z][2][h]; r1 = bc[z][3][h];
     }
+#pragma unroll 4
     for (int b = b_lo; b < b_hi; ++b) {
       const float f = a.feat[(size_t)b * F + k];
       const float* d = sm + (b - b_lo) * J;
@@ -336,9 +337,14 @@ __global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long long n, const long long* __restrict__ step,
                                               float lr, float b1, float b2, float eps, float wd, float gscale) {
-  const double t = (double)(*step);
-  const float bc1 = (float)(1.0 - pow((double)b1, t));
-  const float bc2s = (float)sqrt(1.0 - pow((double)b2, t));
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {                      // bias corrections once per CTA (double pow is slow)
+    const double t = (double)(*step);
+    s_bc[0] = (float)(1.0 - pow((double)b1, t));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)b2, t));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2s = s_bc[1];
   const float step_size = lr / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float pv = p[i];

@@ -30,6 +30,18 @@ struct EncArgs {
   float* h;                   // [R, C] output of the forward
   const float* dh;            // [R, C] gradient wrt h
   float *dW1, *dW2, *dW3, *db3, *dg1, *dbe1, *dg2, *dbe2, *dg3, *dbe3;
+  // Fast path only: phase B1 also finishes the graph-conv blocks' backward (what k_block_bwd_fin does):
+  //   dh = sum_z dxp_z - r0_z*cnt_z(t)*(m1_z + xhat_z*m2_z), written to dh_out, BN0/BN1 affine gradients.
+  struct Fin {
+    int nblk, CP;
+    const float* dxp[2];        // [R, C] per block: dx before the BN0 mean terms
+    const float* tab[2];        // block coefficient table: mu0[CP] r0[CP] ...
+    const double* stats[2];     // block sums (see stg_block_desc.stats)
+    const float* g0[2];
+    float *dg0[2], *db0[2], *dg1[2], *db1[2];
+    int H[2], w[2], stride[2], L[2];
+    float* dh_out;              // [R, C]
+  } fin;
 };
 // stats scratch layout (doubles): forward  [S1: 2*EH][S2: 2*E][S3: 2*C]
 //                                 backward [B3: 2*C][B2: 2*E][B1: 2*EH]

@@ -166,6 +166,19 @@ int build_ctx(Ctx& c, const stg_model_dims* dp, const stg_model_params* pp, cons
   }
   rc = plan_blocks(a, c.plan, err, sizeof(err));
   if (rc) return set_err(rc == -1 ? STG_ERR_INVALID : STG_ERR_UNSUPPORTED, "%s", err);
+  // fast encoder: its first backward phase also finishes the blocks' backward (k_block_bwd_fin fused away)
+  if (training && gp && encoder_fast_available(e)) {
+    a.fin_elsewhere = 1;
+    EncArgs::Fin& f = e.fin;
+    f.nblk = STG_MAX_BLOCKS; f.CP = c.plan.CP;
+    for (int z = 0; z < STG_MAX_BLOCKS; ++z) {
+      const BlkDev& k = a.b[z];
+      f.dxp[z] = k.dxp; f.tab[z] = k.coef; f.stats[z] = k.stats; f.g0[z] = k.g0;
+      f.dg0[z] = k.dg0; f.db0[z] = k.db0; f.dg1[z] = k.dg1; f.db1[z] = k.db1;
+      f.H[z] = k.H; f.w[z] = k.w; f.stride[z] = k.stride; f.L[z] = k.L;
+    }
+    f.dh_out = (float*)(base + c.w.dh);
+  }
 
   // ---- head
   HeadArgs& hd = c.head;
