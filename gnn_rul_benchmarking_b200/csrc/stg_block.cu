@@ -650,13 +650,21 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
   compute_fv<CP, HP>(sm, xs, rows, C);
   __syncthreads();
 
-  const int slot_id = tid / M, i = tid - slot_id * M;
+  // one window per slot of ST = roundup32(M) threads: the phases of a window are separated by
+  // slot-local barriers (__syncwarp / named barrier), not CTA-wide ones
+  const int ST = ((M + 31) / 32) * 32;
+  const int slot_id = tid / ST, i = tid - slot_id * ST;
   const int ji = i / N, ni = i - ji * N;
-  const bool lane_ok = tid < wpc * M;
-  float* Sb = sm.Sb + slot_id * slot;
-  float* invs = sm.invs + slot_id * M;
-  float* dYs = sm.dYs + (size_t)slot_id * M * HP;
+  const bool lane_ok = slot_id < wpc && i < M;
+  const int sslot = slot_id < wpc ? slot_id : 0;          // surplus threads (none by construction) alias slot 0
+  float* Sb = sm.Sb + sslot * slot;
+  float* invs = sm.invs + sslot * M;
+  float* dYs = sm.dYs + (size_t)sslot * M * HP;
   const float invw = 1.f / (float)w;
+  auto slot_sync = [&]() {
+    if (ST == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(slot_id + 1), "r"(ST) : "memory");
+  };
   float dbt_acc[HP];
 #pragma unroll
   for (int h = 0; h < HP; ++h) dbt_acc[h] = 0.f;
@@ -725,7 +733,7 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
         rs *= inv;
         invs[i] = inv;
       }
-      __syncthreads();
+      slot_sync();
       // dV_k = sum_i A[i][k] dY'_i   (this thread plays column k = i)
       float dV[HP];
 #pragma unroll
@@ -744,7 +752,7 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
           }
         }
       }
-      __syncthreads();
+      slot_sync();
       // dS in place (row i)
       if (act) {
         int kk = 0;
@@ -767,7 +775,7 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
           }
         }
       }
-      __syncthreads();
+      slot_sync();
       float dF[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) dF[c] = 0.f;
@@ -785,7 +793,8 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
           }
         }
       }
-      // fold into the per-time-step accumulators, one window offset at a time (no races)
+      // fold into the per-time-step accumulators, one window offset at a time: rows of equal offset are
+      // distinct across the slots, consecutive offsets are ordered by the CTA barrier (no atomics)
       for (int jj = 0; jj < w; ++jj) {
         if (act && ji == jj) {
           float* dst = sm.dFV + ((size_t)(l * s - t_lo) * N + i) * CPH;
@@ -1090,8 +1099,12 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
     size_t cap0 = 74 * 1024;
     if (const char* e = getenv("STG_BWD_CAP_KB")) { const int v2 = atoi(e); if (v2 >= 16) cap0 = (size_t)v2 * 1024; }
     const size_t caps[2] = {cap0, kSmemCap};
+    const int ST = ((M + 31) / 32) * 32;           // threads per window slot in the backward kernel
+    int wpc_b0 = 256 / ST;
+    if (wpc_b0 < 1) wpc_b0 = 1;
+    if (wpc_b0 > 15) wpc_b0 = 15;                   // named barriers 1..15
     for (int sweep = 0; sweep < 2 && !done; ++sweep)
-      for (int wp = wpc; wp >= 1 && !done; --wp) {
+      for (int wp = wpc_b0; wp >= 1 && !done; --wp) {
         int gx = 0;
         const int step_cap = wp + 1;                    // staged time steps of a stride-1, w=2 chunk
         for (int z = 0; z < a.nblk; ++z) {
@@ -1108,7 +1121,7 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
         if (wmax > wp) continue;                        // a chunk would touch more windows than slots
         const size_t sm = carve_bytes(v->CP, v->HP, rows_max, a.C, wp, slot, M, true);
         if (sm <= caps[sweep]) {
-          p.wpc_b = wp; p.smem_b = sm; p.grid_x_b = gx; p.threads_b = ((wp * M + 31) / 32) * 32;
+          p.wpc_b = wp; p.smem_b = sm; p.grid_x_b = gx; p.threads_b = wp * ST;
           done = true;
         }
       }
