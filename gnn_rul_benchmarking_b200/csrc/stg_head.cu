@@ -6,6 +6,7 @@
 //   k_head_bwd1  dfeat[b][k] = sum_j d1[b][j] W1[j][k];  dW1[j][k] += sum_b d1[b][j] feat[b][k]
 //   k_adam       flat multi-tensor Adam with L2 weight decay folded into the gradient
 #include <math.h>
+#include <stdlib.h>
 
 #include "stg_model.cuh"
 
@@ -378,7 +379,8 @@ template <int JP, int SPB>
 void fc1_launch(const HeadArgs& a, cudaStream_t s) {
   const int gx = (a.B + SPB - 1) / SPB;
   int ksplit = (2 * 148 + gx - 1) / gx;              // about two CTAs per SM
-  const int maxsplit = (a.F + 511) / 512;
+  if (const char* e = getenv("STG_FC1_KSPLIT")) { const int v = atoi(e); if (v >= 1) ksplit = v; }
+  const int maxsplit = (a.F + 255) / 256;
   if (ksplit > maxsplit) ksplit = maxsplit;
   if (ksplit < 1) ksplit = 1;
   const int kper = (((a.F + ksplit - 1) / ksplit) + 3) / 4 * 4;
@@ -389,7 +391,8 @@ void fc1_launch(const HeadArgs& a, cudaStream_t s) {
 template <int JP>
 void bwd1_launch(const HeadArgs& a, cudaStream_t s) {
   const int gx = (a.F + 127) / 128;
-  int slices = (2 * 148 + gx - 1) / gx;
+  int slices = (512 + gx - 1) / gx;                  // ~3.5 CTAs of 128 threads per SM (measured optimum on S1)
+  if (const char* e = getenv("STG_BWD1_SLICES")) { const int v = atoi(e); if (v >= 1) slices = v; }
   if (slices > a.B) slices = a.B;
   int bper = (a.B + slices - 1) / slices;
   if ((size_t)bper * a.J * 4 > 40 * 1024) bper = (int)(40 * 1024 / (a.J * 4));
