@@ -199,7 +199,7 @@ def run_native(args):
     alg = get_algorithm_class("FC_STGNN")(cfg, HPARAMS, dev).to(dev)
     alg.train()
     if world > 1:
-        alg.attach_data_parallel()      # one NCCL all-reduce of the flat gradient buffer per step
+        alg.attach_data_parallel(p2p=False if args.nccl else "auto")   # gradient exchange fused into the Adam kernel
     if not args.no_graph:
         alg.enable_cuda_graph(B)        # the step's launches replayed from one CUDA graph
 
@@ -288,6 +288,7 @@ def run_native(args):
         "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][1]}", "global_batch": world * B,
                    "per_gpu_batch": B, "step": "fwd+mse+bwd+adam", "parallelism": f"dp{world}",
                    "cuda_graph": not args.no_graph,
+                   "grad_exchange": ("nvlink-p2p fused with adam" if getattr(alg, "_dp_p2p", False) else "nccl all-reduce") if world > 1 else None,
                    "l2": "flushed between steps (256 MiB memset outside the event pairs)"},
         "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
@@ -309,6 +310,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="windows per GPU per step")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N>1: NCCL all-reduce + Adam instead of the fused NVLink kernel")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

@@ -95,6 +95,9 @@ SIGNATURES = {
     "stg_profile_name": (C.c_char_p, [C.c_int]),
     "stg_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
+MODEL_SIGNATURES["stg_allreduce_adam"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p])
 SIGNATURES.update(MODEL_SIGNATURES)
 
 _lib = None

@@ -45,8 +45,11 @@ class FC_STGNN(Algorithm):
         self.hparams = hparams
         self._dp_group, self._dp_world = None, 1
 
-    def attach_data_parallel(self, group=None, broadcast=True):
-        """Shard windows across ranks, all-reduce ONE flat gradient buffer per step."""
+    def attach_data_parallel(self, group=None, broadcast=True, p2p="auto"):
+        """Shard windows across ranks; ONE exchange of the flat gradient buffer per step.
+        p2p: True / "auto" -> gradients live in NVLink symmetric memory and the optimizer kernel reads the
+        peers' buffers itself (stg_allreduce_adam); False (or when symmetric memory is unavailable with
+        "auto") -> NCCL all-reduce followed by the Adam kernel."""
         import torch.distributed as dist
         self._dp_group, self._dp_world = group, dist.get_world_size(group)
         if broadcast:
@@ -54,6 +57,37 @@ class FC_STGNN(Algorithm):
                 for t in list(self.model.parameters()) + list(self.model.buffers()):
                     dist.broadcast(t, 0, group=group)
         self.optimizer.grad_scale = 1.0 / self._dp_world
+        self._dp_p2p = False
+        if p2p and self._dp_world > 1 and dist.get_backend(group) == "nccl":
+            try:
+                self._attach_p2p(group)
+                self._dp_p2p = True
+            except Exception:
+                if p2p is True:
+                    raise
+
+    def _attach_p2p(self, group):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        eng = self.model.engine
+        fl = eng.flatten()
+        dev = fl["param"].device
+        pg = group if group is not None else dist.group.WORLD
+        gsym = symm_mem.empty(fl["n"], dtype=torch.float32, device=dev)
+        hg = symm_mem.rendezvous(gsym, pg)
+        flags = symm_mem.empty(64, dtype=torch.int32, device=dev)
+        flags.zero_()
+        hf = symm_mem.rendezvous(flags, pg)
+        eng.replace_grad_buffer(gsym)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                       # every rank's flags are zero before anyone signals
+        self.optimizer.attach_p2p(list(hg.buffer_ptrs), list(hf.buffer_ptrs), hg.rank, hg.world_size,
+                                  (gsym, flags, hg, hf))
+        self._p2p_flags = flags
+
+    def p2p_timed_out(self) -> bool:
+        """True if a peer failed to show up inside the fused exchange kernel (bounded wait)."""
+        return bool(getattr(self, "_p2p_flags", None) is not None and int(self._p2p_flags[33]) != 0)
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
     def enable_cuda_graph(self, batch_size):
@@ -111,10 +145,10 @@ class FC_STGNN(Algorithm):
     def _eager_step(self, X, y):
         eng = self.model.engine
         loss = eng.loss_backward(X, y, zero_grad=True)
-        if self._dp_world > 1:
+        if self._dp_world > 1 and not getattr(self, "_dp_p2p", False):
             import torch.distributed as dist
             dist.all_reduce(eng.flat["grad"], op=dist.ReduceOp.SUM, group=self._dp_group)
-        self.optimizer.step()
+        self.optimizer.step()          # p2p: reads the peers' gradients itself
         return loss
 
     def update(self, X, y, epoch=None):

@@ -227,6 +227,17 @@ class ModelEngine:
         self._fp = None
         return self.flat
 
+    def replace_grad_buffer(self, gflat: torch.Tensor) -> None:
+        """Use `gflat` (e.g. NVLink symmetric memory, so peers can read it) as the flat gradient buffer."""
+        fl = self.flatten()
+        if gflat.numel() != fl["n"] or gflat.dtype != torch.float32 or gflat.device != fl["param"].device:
+            raise ValueError("gradient buffer must be float32, on the parameters' device, with the flat size")
+        gflat.zero_()
+        for (_, t), off in zip(param_tensors(self.model), fl["offsets"]):
+            t.grad = gflat[off:off + t.numel()].view_as(t)
+        fl["grad"] = gflat
+        fl["gstruct"] = self.grad_struct(gflat, fl["offsets"])
+
     def loss_backward(self, X: torch.Tensor, y: torch.Tensor, zero_grad: bool = True):
         """forward -> MSE -> backward in one C call; gradients land in the flat gradient buffer.
         Returns the loss as a 0-dim device tensor (no host synchronisation)."""
@@ -304,6 +315,14 @@ class StgAdam(torch.optim.Optimizer):
         self.engine = engine
         self._st = None
         self.grad_scale = 1.0
+        self._p2p = None           # (grad_ptrs, flag_ptrs, rank, world, keepalive) once attach_p2p() ran
+
+    def attach_p2p(self, grad_ptrs, flag_ptrs, rank, world, keepalive) -> None:
+        """Exchange gradients inside the optimizer kernel: peers' flat gradient buffers are read over
+        NVLink (stg_allreduce_adam) instead of an NCCL all-reduce followed by the Adam kernel."""
+        gp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in grad_ptrs])
+        fp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in flag_ptrs])
+        self._p2p = (gp, fp, int(rank), int(world), keepalive)
 
     def _state(self):
         fl = self.engine.flatten()
@@ -340,6 +359,14 @@ class StgAdam(torch.optim.Optimizer):
             if p.grad is not None and p.grad.data_ptr() != fl["grad"].data_ptr() + 4 * off:
                 fl["grad"][off:off + p.numel()].view_as(p).copy_(p.grad)
         lib = _lib.load()
+        if self._p2p is not None:
+            gp, fp, rank, world, _ = self._p2p
+            with torch.cuda.device(fl["param"].device):
+                _lib.check(lib.stg_allreduce_adam(fl["param"].data_ptr(), st["exp_avg"].data_ptr(),
+                                                  st["exp_avg_sq"].data_ptr(), fl["n"], st["step"].data_ptr(), gp, fp,
+                                                  rank, world, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                                                  g["weight_decay"], _stream()), "stg_allreduce_adam")
+            return None
         with torch.cuda.device(fl["param"].device):
             _lib.check(lib.stg_adam_step(fl["param"].data_ptr(), fl["grad"].data_ptr(), st["exp_avg"].data_ptr(),
                                          st["exp_avg_sq"].data_ptr(), fl["n"], st["step"].data_ptr(), g["lr"],

@@ -212,6 +212,16 @@ int stg_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, f
                   int64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
                   float grad_scale, void* stream);
 
+/* Data-parallel step (the reference has no distributed code): one-shot
+ * all-reduce of the flat gradient buffers over NVLink peer memory fused with the Adam update.
+ * grad_ptrs[r] / flag_ptrs[r] (host arrays of `world` device pointers) address rank r's gradient
+ * buffer (n floats) and flag block (>= 64 zero-initialised uint32) and must be peer-mapped on this
+ * device (e.g. torch symmetric memory).  Every rank must call it once per step with the same n;
+ * the kernel waits (bounded, ~2 s) for all peers.  flag word 33 != 0 afterwards means a peer timed out. */
+int stg_allreduce_adam(float* param_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, int64_t* step_dev,
+                       const float* const* grad_ptrs, uint32_t* const* flag_ptrs, int rank, int world, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Per-kernel timing (measurement aid, no reference counterpart: the reference has no profiler,
  * SURVEY.md section 5).  When enabled, every kernel launch of this library is bracketed by a

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, p2p=False):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -25,7 +25,8 @@ def _worker(rank, world, port, q):
     alg = get_algorithm_class("FC_STGNN")(CONFIGS["FD004"], TRAIN_PARAMS, dev).to(dev)
     alg.model.positional_encoding.dropout.p = 0.0
     alg.train()
-    alg.attach_data_parallel()
+    alg.attach_data_parallel(p2p=p2p)
+    assert alg._dp_p2p == bool(p2p)
     g = torch.Generator().manual_seed(3)
     X, y = torch.rand(16, 14, 50, generator=g), torch.rand(16, 1, generator=g)
     losses = []
@@ -35,6 +36,7 @@ def _worker(rank, world, port, q):
     flat = alg.model.engine.flat["param"].clone()
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
+    assert not alg.p2p_timed_out()
     if rank == 0:
         q.put((losses, [t.cpu() for t in gathered]))
     dist.destroy_process_group()
@@ -54,3 +56,29 @@ def test_two_gpu_replicas_stay_identical():
         assert p.exitcode == 0
     assert all(l == l for l in losses)                 # finite
     assert torch.equal(params[0], params[1])           # same averaged gradient -> same Adam update
+
+
+def _run(p2p):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000) + (7 if p2p else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, p2p)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_fused_nvlink_exchange_matches_nccl():
+    """stg_allreduce_adam (peers' gradients read over NVLink inside the Adam kernel) == NCCL all-reduce +
+    Adam.  Replicas of one run are bit-identical (same sums in the same rank order); two separate runs
+    agree to float-atomic summation noise of the forward/backward kernels."""
+    l_nccl, p_nccl = _run(False)
+    l_p2p, p_p2p = _run(True)
+    assert torch.equal(p_p2p[0], p_p2p[1])             # replicas identical
+    assert all(abs(a - b) < 1e-6 for a, b in zip(l_nccl, l_p2p))
+    assert float((p_nccl[0] - p_p2p[0]).abs().max()) < 2e-6
