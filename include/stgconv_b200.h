@@ -212,6 +212,12 @@ int stg_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, f
                   int64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
                   float grad_scale, void* stream);
 
+/* Evaluation metrics (utils.py:136-169, called every epoch from trainer.py:119-121): ACCUMULATES into
+ * out4_dev (4 doubles, caller zeroes): [0] sum of Score_v1 terms, [1] sum of Score_v2 terms,
+ * [2] sum |pred-real|, [3] sum (pred-real)^2.  Score_v2 average, MAE and RMSE follow as
+ * out[1]/n, out[2]/n*max_rul, sqrt(out[3]/n)*max_rul. */
+int stg_metrics(const float* pred_dev, const float* real_dev, int64_t n, float max_rul, double* out4_dev, void* stream);
+
 /* Data-parallel step (the reference has no distributed code): one-shot
  * all-reduce of the flat gradient buffers over NVLink peer memory fused with the Adam update.
  * grad_ptrs[r] / flag_ptrs[r] (host arrays of `world` device pointers) address rank r's gradient

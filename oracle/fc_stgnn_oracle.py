@@ -372,6 +372,27 @@ def score_v1(pred, real, max_rul: float) -> Tuple[float, float]:
     return float(s), float(s / pred.numel())
 
 
+def score_v2(pred, real) -> float:
+    """utils.py:157-169 (relative-error score, averaged), vectorised."""
+    pred = torch.as_tensor(pred, dtype=torch.float64).reshape(-1)
+    real = torch.as_tensor(real, dtype=torch.float64).reshape(-1)
+    err = (real - pred) / (real + 1e-8) * 100.0
+    s = torch.where(err <= 0, torch.exp(-math.log(0.5) * (err / 5.0)), torch.exp(math.log(0.5) * (err / 20.0)))
+    return float(s.mean())
+
+
+def mae(pred, real, max_rul: float) -> float:
+    """utils.py:153-155: mean absolute error * max_rul."""
+    pred = torch.as_tensor(pred, dtype=torch.float64).reshape(-1)
+    real = torch.as_tensor(real, dtype=torch.float64).reshape(-1)
+    return float((pred - real).abs().mean() * max_rul)
+
+
+def calc_metrics(pred, real, max_rul: float):
+    """utils.py:191-201 _calc_metrics -> (Scores_v1, Scores_v2, MAE, RMSE)."""
+    return score_v1(pred, real, max_rul)[0], score_v2(pred, real), mae(pred, real, max_rul), rmse(pred, real, max_rul)
+
+
 CONFIGS = {
     # configs/hparams.py:149-151 (CMAPSS FD004) -- the metric config "S1"
     "FD004": dict(patch_size=2, num_patch=25, encoder_time_out=4, encoder_hidden_dim=8, encoder_out_dim=6,

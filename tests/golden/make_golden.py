@@ -129,7 +129,42 @@ def block_golden(tag, B, T, N, C, H, stride, seed):
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def aux_golden():
+    """Reference metrics (utils.py:136-201) and reference data path (dataloader/dataloader.py) outputs."""
+    ref_shims.install()
+    import utils as ref_utils                                    # noqa: E402  (reference module)
+    from dataloader.dataloader import Load_Dataset               # noqa: E402
+    rng = np.random.default_rng(0)
+    out = {}
+    for i, n in enumerate((1, 7, 100, 257)):
+        real = rng.uniform(0.0, 1.0, n).astype(np.float32)
+        pred = (real + rng.normal(0, 0.15, n)).astype(np.float32)
+        s1, s2, mae, rmse = ref_utils._calc_metrics(pred, real, 125)
+        sa, avg, rmse_a = ref_utils._calc_metrics_aeroengine(pred, real, 125)
+        sb, mae_b, rmse_b = ref_utils._calc_metrics_bearing(pred, real, 125)
+        out[f"m{i}/pred"], out[f"m{i}/real"] = pred, real
+        out[f"m{i}/all"] = np.array([s1, s2, mae, rmse], dtype=np.float64)
+        out[f"m{i}/aero"] = np.array([sa, avg, rmse_a], dtype=np.float64)
+        out[f"m{i}/bearing"] = np.array([sb, mae_b, rmse_b], dtype=np.float64)
+    # data path: C-MAPSS on-disk format (list of [L, C] float32 windows) -> channel-first tensors, and the
+    # batch order of DataLoader(shuffle=True) after torch.manual_seed(3)
+    samples = [rng.uniform(0, 1, (50, 14)).astype(np.float32) for _ in range(23)]
+    labels = rng.uniform(0, 1, (23, 1)).astype(np.float32)
+    ds = Load_Dataset(samples, labels, False)
+    torch.manual_seed(3)
+    dl = torch.utils.data.DataLoader(dataset=ds, batch_size=5, shuffle=True, drop_last=False, num_workers=0)
+    xs, ys = zip(*[(x, y) for x, y in dl])
+    out["data/samples"] = np.stack(samples)
+    out["data/labels"] = labels
+    out["data/x_batches"] = _np(torch.cat(xs))
+    out["data/y_batches"] = _np(torch.cat(ys))
+    path = os.path.join(OUT, "aux_metrics_data.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
+    aux_golden()
     model_golden("FD004", CONFIGS["FD004"], 6, 0)
     model_golden("FD004", CONFIGS["FD004"], 3, 1)
     model_golden("FD001", CONFIGS["FD001"], 4, 0)
