@@ -99,6 +99,10 @@ MODEL_SIGNATURES["stg_allreduce_adam"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_
                                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p])
 MODEL_SIGNATURES["stg_metrics"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p])
+MODEL_SIGNATURES["stg_adj_forward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p])
+MODEL_SIGNATURES["stg_adj_backward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                                  C.c_int, C.c_void_p, C.c_void_p])
 SIGNATURES.update(MODEL_SIGNATURES)
 
 _lib = None

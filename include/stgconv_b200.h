@@ -212,6 +212,21 @@ int stg_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, f
                   int64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
                   float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense per-graph adjacency builders of the sibling models (primitives A2-A4):
+ * x [G, N, F] -> adj [G, N, N], forward and backward (dx given dadj).
+ *   STG_ADJ_PCC     pcc_graph_construction        models/ST_GCN/Model.py:53-71 (also ST_Conv, LOGO, DVGTformer)
+ *   STG_ADJ_COSINE  cosine_distance               models/HAGCN/Model.py:122-127, models/SAGCN/Model.py:74-79
+ *   STG_ADJ_GAUSS   exp(-cdist(x, x))             models/ASTGCNN/Model.py:193-194 (its Linear P stays a GEMM)
+ *   STG_ADJ_GAUSS2  exp(-cdist^2), top_k per row  models/STGNN/Model.py:8-25 (top_k <= 0 or >= N: dense)
+ * mask_dev (optional, GAUSS2): 0/1 bytes of the kept entries.  The backward takes the forward's adj
+ * (masked entries are zero and carry no gradient). */
+enum { STG_ADJ_PCC = 0, STG_ADJ_COSINE = 1, STG_ADJ_GAUSS = 2, STG_ADJ_GAUSS2 = 3 };
+int stg_adj_forward(int kind, const float* x_dev, int64_t G, int N, int F, int top_k, float* adj_dev,
+                    unsigned char* mask_dev, void* stream);
+int stg_adj_backward(int kind, const float* x_dev, const float* adj_dev, const float* dadj_dev, int64_t G, int N,
+                     int F, float* dx_dev, void* stream);
+
 /* Evaluation metrics (utils.py:136-169, called every epoch from trainer.py:119-121): ACCUMULATES into
  * out4_dev (4 doubles, caller zeroes): [0] sum of Score_v1 terms, [1] sum of Score_v2 terms,
  * [2] sum |pred-real|, [3] sum (pred-real)^2.  Score_v2 average, MAE and RMSE follow as

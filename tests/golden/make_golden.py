@@ -158,6 +158,30 @@ def aux_golden():
     out["data/labels"] = labels
     out["data/x_batches"] = _np(torch.cat(xs))
     out["data/y_batches"] = _np(torch.cat(ys))
+    # sibling adjacency builders: reference functions, outputs and input gradients
+    from models.ST_GCN.Model import pcc_graph_construction           # noqa: E402
+    from models.HAGCN.Model import cosine_distance                   # noqa: E402
+    from models.ASTGCNN.Model import construct_graph                 # noqa: E402
+    from models.STGNN.Model import compute_adjacency_matrix          # noqa: E402
+    tg = torch.Generator().manual_seed(11)
+
+    def adj_case(tag, fn, shape):
+        x = torch.randn(*shape, generator=tg).requires_grad_(True)
+        a = fn(x)
+        da = torch.randn(a.shape, generator=tg)
+        (a * da).sum().backward()
+        out[f"adj/{tag}/x"], out[f"adj/{tag}/a"] = _np(x), _np(a)
+        out[f"adj/{tag}/da"], out[f"adj/{tag}/dx"] = _np(da), _np(x.grad)
+
+    adj_case("pcc", pcc_graph_construction, (5, 10, 40))                 # ST_GCN: 10 statistic nodes x 40 patches
+    adj_case("cosine", cosine_distance, (4, 14, 60))                     # HAGCN: 14 sensors x 60 features
+    adj_case("cosine_big", cosine_distance, (2, 160, 40))                # SAGCN: 160 patch nodes
+    cg = construct_graph(50)
+    with torch.no_grad():
+        cg.P.weight.copy_(torch.eye(50))                                 # P = I: pins exp(-cdist) itself
+    adj_case("gauss", cg, (3, 20, 50))                                   # ASTGCNN N-CMAPSS
+    adj_case("gauss2_top10", lambda t: compute_adjacency_matrix(t, 10), (2, 3, 14, 5))   # STGNN
+    adj_case("gauss2_top3", lambda t: compute_adjacency_matrix(0.3 * t, 3), (2, 1, 14, 50))
     path = os.path.join(OUT, "aux_metrics_data.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -72,3 +72,28 @@ def test_device_metrics_match_reference(i):
     assert np.allclose(metrics.calc_metrics_bearing(pred, real, 125.0), Z[f"m{i}/bearing"], rtol=5e-6, atol=1e-7)
     with pytest.raises(RuntimeError):
         metrics.calc_metrics(pred.cpu(), real.cpu(), 125.0)
+
+
+ADJ_CASES = ["pcc", "cosine", "cosine_big", "gauss", "gauss2_top10", "gauss2_top3"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ADJ_CASES)
+def test_adjacency_builders_match_reference(tag):
+    """SURVEY 2.2 primitives A2-A4 (sibling models): device forward / backward vs the reference functions'
+    own outputs and autograd gradients."""
+    from gnn_rul_benchmarking_b200 import primitives as P
+    dev = torch.device("cuda:0")
+    fn = {"pcc": P.pcc_graph_construction, "cosine": P.cosine_distance, "cosine_big": P.cosine_distance,
+          "gauss": P.gaussian_adjacency, "gauss2_top10": lambda t: P.compute_adjacency_matrix(t, 10),
+          "gauss2_top3": lambda t: P.compute_adjacency_matrix(0.3 * t, 3)}[tag]
+    x = torch.from_numpy(Z[f"adj/{tag}/x"]).to(dev).requires_grad_(True)
+    a = fn(x)
+    ref_a = torch.from_numpy(Z[f"adj/{tag}/a"])
+    assert a.shape == ref_a.shape
+    assert float((a.detach().cpu() - ref_a).abs().max()) < 2e-5
+    (a * torch.from_numpy(Z[f"adj/{tag}/da"]).to(dev)).sum().backward()
+    ref_dx = torch.from_numpy(Z[f"adj/{tag}/dx"])
+    assert float((x.grad.cpu() - ref_dx).abs().max()) < 1e-4 * max(1.0, float(ref_dx.abs().max()))
+    with pytest.raises(RuntimeError):
+        P.cosine_distance(torch.randn(2, 4, 8))           # CPU tensor: no fallback
