@@ -103,6 +103,10 @@ MODEL_SIGNATURES["stg_adj_forward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_int64,
                                                  C.c_void_p, C.c_void_p])
 MODEL_SIGNATURES["stg_adj_backward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                                   C.c_int, C.c_void_p, C.c_void_p])
+MODEL_SIGNATURES["stg_agg_forward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                                 C.c_void_p])
+MODEL_SIGNATURES["stg_agg_backward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
 SIGNATURES.update(MODEL_SIGNATURES)
 
 _lib = None

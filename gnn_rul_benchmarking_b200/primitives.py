@@ -64,3 +64,71 @@ def gaussian_adjacency(PX: torch.Tensor) -> torch.Tensor:
 def compute_adjacency_matrix(input: torch.Tensor, top_k: int) -> torch.Tensor:
     """models/STGNN/Model.py:8-25: input [bs, L, N, f] -> exp(-cdist^2) with the top_k entries of each row kept."""
     return _Adjacency.apply(input, ADJ_GAUSS2, top_k)
+
+
+# ------------------------------------------------------------------------------------------ M2 / M3
+AGG_GCN, AGG_CHEB3 = 0, 1
+
+
+class _Aggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, adj, kind):
+        if not (x.is_cuda and adj.is_cuda):
+            raise RuntimeError("graph aggregation runs on the device (no CPU fallback)")
+        G, N, F = x.shape
+        xc, ac = x.contiguous(), adj.contiguous()
+        out = torch.empty((G, N, F) if kind == AGG_GCN else (G, 3, N, F), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().stg_agg_forward(kind, xc.data_ptr(), ac.data_ptr(), G, N, F, out.data_ptr(), _stream()),
+                       "stg_agg_forward")
+        ctx.save_for_backward(xc, ac)
+        ctx.kind = kind
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, ac = ctx.saved_tensors
+        G, N, F = xc.shape
+        dout = dout.contiguous()
+        dx, dadj = torch.empty_like(xc), torch.empty_like(ac)
+        with torch.cuda.device(xc.device):
+            _lib.check(_lib.load().stg_agg_backward(ctx.kind, xc.data_ptr(), ac.data_ptr(), dout.data_ptr(), G, N, F,
+                                                    dx.data_ptr(), dadj.data_ptr(), _stream()), "stg_agg_backward")
+        return dx, dadj, None
+
+
+def gcn_aggregate(X: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
+    """D^-1/2 (A+I) D^-1/2 X of GCNLayer.forward (models/STMSGCN/Model.py:39-47, SAGCN:86-93, RGCNU:12-19)."""
+    return _Aggregate.apply(X, A, AGG_GCN)
+
+
+def cheb_terms(x: torch.Tensor, adj_matrix: torch.Tensor) -> torch.Tensor:
+    """[T0, T1, T2] = [x, A x, 2 A (A x) - x] of ChebNet.forward, K=3 (models/ASTGCNN/Model.py:218-228) -> [bs,3,N,f]."""
+    return _Aggregate.apply(x, adj_matrix, AGG_CHEB3)
+
+
+class GCNLayer(torch.nn.Module):
+    """models/STMSGCN/Model.py:34-49: leaky_relu(Linear(D^-1/2 (A+I) D^-1/2 X)); same parameter names."""
+
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        self.linear = torch.nn.Linear(in_features, out_features)
+
+    def forward(self, X, A):
+        return torch.nn.functional.leaky_relu(self.linear(gcn_aggregate(X, A)))
+
+
+class ChebNet(torch.nn.Module):
+    """models/ASTGCNN/Model.py:198-230 (K = 3, the only value the reference configures); same parameter name."""
+
+    def __init__(self, in_channels, out_channels, K):
+        super().__init__()
+        if K != 3:
+            raise NotImplementedError("the reference hyper-parameters use K = 3 (configs/hparams.py)")
+        self.in_channels, self.out_channels, self.K = in_channels, out_channels, K
+        self.filters = torch.nn.Parameter(torch.empty(K, in_channels, out_channels))
+        torch.nn.init.xavier_uniform_(self.filters)
+
+    def forward(self, x, adj_matrix):
+        T = cheb_terms(x, adj_matrix)                                  # [bs, 3, N, f]
+        return torch.einsum("bknf,kfo->bno", T, self.filters)

@@ -227,6 +227,17 @@ int stg_adj_forward(int kind, const float* x_dev, int64_t G, int N, int F, int t
 int stg_adj_backward(int kind, const float* x_dev, const float* adj_dev, const float* dadj_dev, int64_t G, int N,
                      int F, float* dx_dev, void* stream);
 
+/* Dense graph aggregation of the sibling models (primitives M2 / M3); the learnable
+ * projections that follow are plain GEMMs and stay with the caller.
+ *   STG_AGG_GCN    out [G,N,F]   = D^-1/2 (A+I) D^-1/2 X       models/SAGCN/Model.py:81-95, STMSGCN:34-49, RGCNU:7-21
+ *   STG_AGG_CHEB3  out [G,3,N,F] = [X, A X, 2 A (A X) - X]     models/ASTGCNN/Model.py:212-228, STGNN:43-59
+ * backward: dout (same shape as out) -> dx [G,N,F], dadj [G,N,N]. */
+enum { STG_AGG_GCN = 0, STG_AGG_CHEB3 = 1 };
+int stg_agg_forward(int kind, const float* x_dev, const float* adj_dev, int64_t G, int N, int F, float* out_dev,
+                    void* stream);
+int stg_agg_backward(int kind, const float* x_dev, const float* adj_dev, const float* dout_dev, int64_t G, int N,
+                     int F, float* dx_dev, float* dadj_dev, void* stream);
+
 /* Evaluation metrics (utils.py:136-169, called every epoch from trainer.py:119-121): ACCUMULATES into
  * out4_dev (4 doubles, caller zeroes): [0] sum of Score_v1 terms, [1] sum of Score_v2 terms,
  * [2] sum |pred-real|, [3] sum (pred-real)^2.  Score_v2 average, MAE and RMSE follow as

@@ -182,6 +182,29 @@ def aux_golden():
     adj_case("gauss", cg, (3, 20, 50))                                   # ASTGCNN N-CMAPSS
     adj_case("gauss2_top10", lambda t: compute_adjacency_matrix(t, 10), (2, 3, 14, 5))   # STGNN
     adj_case("gauss2_top3", lambda t: compute_adjacency_matrix(0.3 * t, 3), (2, 1, 14, 50))
+    # graph aggregation layers: reference modules, outputs and all gradients
+    from models.STMSGCN.Model import GCNLayer                        # noqa: E402
+    from models.ASTGCNN.Model import ChebNet                         # noqa: E402
+
+    def layer_case(tag, layer, x_shape, pos_adj):
+        x = torch.randn(*x_shape, generator=tg).requires_grad_(True)
+        n = x_shape[1]
+        a = torch.rand(x_shape[0], n, n, generator=tg) if pos_adj else 0.3 * torch.randn(x_shape[0], n, n, generator=tg)
+        a.requires_grad_(True)
+        y = layer(x, a)
+        dy = torch.randn(y.shape, generator=tg)
+        (y * dy).sum().backward()
+        out[f"layer/{tag}/x"], out[f"layer/{tag}/a"], out[f"layer/{tag}/y"] = _np(x), _np(a), _np(y)
+        out[f"layer/{tag}/dy"], out[f"layer/{tag}/dx"], out[f"layer/{tag}/da"] = _np(dy), _np(x.grad), _np(a.grad)
+        for k, p in layer.named_parameters():
+            out[f"layer/{tag}/p/{k}"] = _np(p)
+            out[f"layer/{tag}/g/{k}"] = _np(p.grad)
+
+    torch.manual_seed(5)
+    layer_case("gcn", GCNLayer(5, 7), (4, 9, 5), True)                 # STMSGCN-style, positive degrees
+    layer_case("gcn_wide", GCNLayer(40, 100), (2, 32, 40), True)       # SAGCN-sized
+    layer_case("cheb", ChebNet(50, 64, 3), (3, 14, 50), False)         # ASTGCNN FD004
+    layer_case("cheb_small", ChebNet(5, 8, 3), (6, 20, 5), False)      # STGNN N-CMAPSS patch features
     path = os.path.join(OUT, "aux_metrics_data.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -97,3 +97,30 @@ def test_adjacency_builders_match_reference(tag):
     assert float((x.grad.cpu() - ref_dx).abs().max()) < 1e-4 * max(1.0, float(ref_dx.abs().max()))
     with pytest.raises(RuntimeError):
         P.cosine_distance(torch.randn(2, 4, 8))           # CPU tensor: no fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["gcn", "gcn_wide", "cheb", "cheb_small"])
+def test_aggregation_layers_match_reference(tag):
+    """SURVEY 2.2 primitives M2 / M3: GCNLayer (STMSGCN) and ChebNet (ASTGCNN) mirrors -- native aggregation
+    + library GEMM -- vs the reference modules' outputs and every gradient (dX, dA, parameters)."""
+    from gnn_rul_benchmarking_b200 import primitives as P
+    dev = torch.device("cuda:0")
+    pre = f"layer/{tag}/"
+    params = {k[len(pre) + 2:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith(pre + "p/")}
+    if tag.startswith("gcn"):
+        layer = P.GCNLayer(params["linear.weight"].shape[1], params["linear.weight"].shape[0])
+    else:
+        layer = P.ChebNet(params["filters"].shape[1], params["filters"].shape[2], 3)
+    layer.load_state_dict(params, strict=True)
+    layer = layer.to(dev)
+    x = torch.from_numpy(Z[pre + "x"]).to(dev).requires_grad_(True)
+    a = torch.from_numpy(Z[pre + "a"]).to(dev).requires_grad_(True)
+    y = layer(x, a)
+    rel = lambda got, ref: float((got.cpu() - ref).abs().max()) / max(1.0, float(ref.abs().max()))
+    assert rel(y.detach(), torch.from_numpy(Z[pre + "y"])) < 2e-5
+    (y * torch.from_numpy(Z[pre + "dy"]).to(dev)).sum().backward()
+    assert rel(x.grad, torch.from_numpy(Z[pre + "dx"])) < 1e-4
+    assert rel(a.grad, torch.from_numpy(Z[pre + "da"])) < 1e-4
+    for k, p in layer.named_parameters():
+        assert rel(p.grad, torch.from_numpy(Z[pre + "g/" + k])) < 1e-4, k
