@@ -246,18 +246,142 @@ static size_t tail_smem(int J, int H, int TB) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Tail of the head (fc2..fc4 + loss/backward) for the samples [b_lo, b_lo+nb) of one k_head_bwd1 CTA:
+// every CTA of a sample slice recomputes it (a few thousand MACs) instead of waiting for a separate
+// k_head_tail launch; only the slice's first CTA (owner) accumulates the tail's parameter gradients,
+// the loss and the predictions.  Result: d1s[(b-b_lo)*J + j] = dLoss/dz1.  All threads must call it.
+template <bool HAVE_Y>
+__device__ void tail_slice(const HeadArgs& a, int b_lo, int nb, float* d1s, float* scr, bool owner) {
+  const int J = a.J, H = a.H, tid = threadIdx.x, nt = blockDim.x;
+  const int NBP = nb + 1;
+  float* W2 = scr;                float* W3 = W2 + J * J;        float* W4 = W3 + H * J;
+  float* bb = W4 + H;             float* a1 = bb + J + H + 1;    float* a2 = a1 + J * NBP;
+  float* a3 = a2 + J * NBP;       float* dd2 = a3 + H * NBP;     float* dd3 = dd2 + J * NBP;
+  float* dps = dd3 + H * NBP;
+  for (int i = tid; i < J * J; i += nt) W2[i] = a.W2[i];
+  for (int i = tid; i < H * J; i += nt) W3[i] = a.W3[i];
+  for (int i = tid; i < H; i += nt) W4[i] = a.W4[i];
+  for (int i = tid; i < J; i += nt) bb[i] = a.b2[i];
+  for (int i = tid; i < H; i += nt) bb[J + i] = a.b3[i];
+  if (tid == 0) bb[J + H] = a.b4[0];
+  for (int e = tid; e < nb * J; e += nt) a1[(e % J) * NBP + e / J] = fmaxf(a.z1[(size_t)b_lo * J + e], 0.f);
+  __syncthreads();
+  for (int e = tid; e < nb * J; e += nt) {                 // fc2 + ReLU
+    const int sl = e / J, i = e - sl * J;
+    float v = bb[i];
+    for (int j = 0; j < J; ++j) v = fmaf(W2[i * J + j], a1[j * NBP + sl], v);
+    a2[i * NBP + sl] = fmaxf(v, 0.f);
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * H; e += nt) {                 // fc3 + ReLU
+    const int sl = e / H, i = e - sl * H;
+    float v = bb[J + i];
+    for (int j = 0; j < J; ++j) v = fmaf(W3[i * J + j], a2[j * NBP + sl], v);
+    a3[i * NBP + sl] = fmaxf(v, 0.f);
+  }
+  __syncthreads();
+  float lossv = 0.f;
+  for (int sl = tid; sl < nb; sl += nt) {                  // fc4, loss, dpred
+    float pred = bb[J + H];
+    for (int i = 0; i < H; ++i) pred = fmaf(W4[i], a3[i * NBP + sl], pred);
+    const int b = b_lo + sl;
+    float dp;
+    if (HAVE_Y) {
+      const float e = pred - a.y[b];
+      lossv += e * e / (float)a.B;
+      dp = 2.f * e / (float)a.B;
+    } else {
+      dp = a.dpred[b];
+    }
+    dps[sl] = dp;
+    if (owner && a.pred) a.pred[b] = pred;
+  }
+  if (HAVE_Y && owner) {
+    lossv = warp_sum(lossv);
+    if ((tid & 31) == 0 && lossv != 0.f && a.loss) atomicAdd(a.loss, lossv);
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * H; e += nt) {
+    const int sl = e / H, i = e - sl * H;
+    dd3[i * NBP + sl] = a3[i * NBP + sl] > 0.f ? dps[sl] * W4[i] : 0.f;
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * J; e += nt) {
+    const int sl = e / J, j = e - sl * J;
+    float v = 0.f;
+    if (a2[j * NBP + sl] > 0.f)
+      for (int i = 0; i < H; ++i) v = fmaf(dd3[i * NBP + sl], W3[i * J + j], v);
+    dd2[j * NBP + sl] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * J; e += nt) {
+    const int sl = e / J, j = e - sl * J;
+    float v = 0.f;
+    if (a1[j * NBP + sl] > 0.f)
+      for (int i = 0; i < J; ++i) v = fmaf(dd2[i * NBP + sl], W2[i * J + j], v);
+    d1s[sl * J + j] = v;
+  }
+  __syncthreads();
+  if (!owner) return;
+  // parameter gradients of the tail over this slice's samples: one owner thread per entry
+  const int nacc = J * J + J + H * J + H + H + 1 + J;
+  for (int e = tid; e < nacc; e += nt) {
+    float v = 0.f;
+    if (e < J * J) {
+      const int i = e / J, j = e - i * J;
+      for (int r = 0; r < nb; ++r) v = fmaf(dd2[i * NBP + r], a1[j * NBP + r], v);
+      atomicAdd(&a.dW2[e], v);
+    } else if (e < J * J + J) {
+      const int i = e - J * J;
+      for (int r = 0; r < nb; ++r) v += dd2[i * NBP + r];
+      atomicAdd(&a.db2[i], v);
+    } else if (e < J * J + J + H * J) {
+      const int q = e - (J * J + J), i = q / J, j = q - i * J;
+      for (int r = 0; r < nb; ++r) v = fmaf(dd3[i * NBP + r], a2[j * NBP + r], v);
+      atomicAdd(&a.dW3[q], v);
+    } else if (e < J * J + J + H * J + H) {
+      const int i = e - (J * J + J + H * J);
+      for (int r = 0; r < nb; ++r) v += dd3[i * NBP + r];
+      atomicAdd(&a.db3[i], v);
+    } else if (e < J * J + J + H * J + 2 * H) {
+      const int i = e - (J * J + J + H * J + H);
+      for (int r = 0; r < nb; ++r) v = fmaf(dps[r], a3[i * NBP + r], v);
+      atomicAdd(&a.dW4[i], v);
+    } else if (e == J * J + J + H * J + 2 * H) {
+      for (int r = 0; r < nb; ++r) v += dps[r];
+      atomicAdd(&a.db4[0], v);
+    } else {
+      const int j = e - (J * J + J + H * J + 2 * H + 1);
+      for (int r = 0; r < nb; ++r) v += d1s[r * J + j];
+      atomicAdd(&a.db1[j], v);
+    }
+  }
+}
+
+static size_t tail_slice_floats(int J, int H, int nb) {
+  const size_t NBP = nb + 1;
+  return (size_t)J * J + (size_t)H * J + H + J + H + 1 + (size_t)(3 * J + 2 * H + 1) * NBP + 4;
+}
+
+// ------------------------------------------------------------------------------------------
 // grid (ceil(F/128), BS); thread = one feature column k, samples [b_lo, b_hi) of slice blockIdx.y
 //   dfeat[b][k] = sum_j d1[b][j] W1[j][k];  dW1[j][k] += sum_b d1[b][j] feat[b][k]
 // FUSED: also the BatchNorm-1 backward sums of the graph-conv blocks (what k_block_bwd_stats computes):
 //   stats[2H+h] += sum dYn, stats[3H+h] += sum dYn*Yhat, with dYn = dfeat/w * lrelu'(BN1(Y')).
-template <int JP, bool FUSED>
+template <int JP, bool FUSED, int TAIL>      // TAIL: 0 = d1 given, 1 = tail from dpred, 2 = tail with MSE loss
 __global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
-  extern __shared__ __align__(16) float sm[];   // d1 slice [bper][J]
+  extern __shared__ __align__(16) float sm[];   // d1 slice [bper][J] (+ tail scratch)
   __shared__ float bc[2][4][64];
   __shared__ float sred[2][2][64];
   const int J = a.J, F = a.F, tid = threadIdx.x;
   const int b_lo = blockIdx.y * bper, b_hi = min(a.B, b_lo + bper);
-  for (int i = tid; i < (b_hi - b_lo) * J; i += blockDim.x) sm[i] = a.d1[(size_t)b_lo * J + i];
+  if (TAIL == 0) {
+    for (int i = tid; i < (b_hi - b_lo) * J; i += blockDim.x) sm[i] = a.d1[(size_t)b_lo * J + i];
+  } else {
+    float* scr = sm + ((bper * J + 3) / 4) * 4;
+    if (TAIL == 2) tail_slice<true>(a, b_lo, b_hi - b_lo, sm, scr, blockIdx.x == 0);
+    else tail_slice<false>(a, b_lo, b_hi - b_lo, sm, scr, blockIdx.x == 0);
+  }
   if (FUSED) {
     head_bn1(a, bc, false);
     for (int i = tid; i < 2 * 2 * 64; i += blockDim.x) (&sred[0][0][0])[i] = 0.f;
@@ -397,8 +521,15 @@ void bwd1_launch(const HeadArgs& a, cudaStream_t s) {
   int bper = (a.B + slices - 1) / slices;
   if ((size_t)bper * a.J * 4 > 40 * 1024) bper = (int)(40 * 1024 / (a.J * 4));
   slices = (a.B + bper - 1) / bper;
-  if (a.fused_blocks) k_head_bwd1<JP, true><<<dim3(gx, slices), 128, (size_t)bper * a.J * 4, s>>>(a, bper);
-  else k_head_bwd1<JP, false><<<dim3(gx, slices), 128, (size_t)bper * a.J * 4, s>>>(a, bper);
+  const size_t sm_d1 = (size_t)((bper * a.J + 3) / 4) * 4 * 4;
+  if (a.fused_blocks) {
+    // model path: the tail (fc2..fc4, loss, its backward) is recomputed per slice inside this kernel
+    const size_t smt = sm_d1 + tail_slice_floats(a.J, a.H, bper) * 4;
+    if (a.y) k_head_bwd1<JP, true, 2><<<dim3(gx, slices), 128, smt, s>>>(a, bper);
+    else k_head_bwd1<JP, true, 1><<<dim3(gx, slices), 128, smt, s>>>(a, bper);
+  } else {
+    k_head_bwd1<JP, false, 0><<<dim3(gx, slices), 128, sm_d1, s>>>(a, bper);
+  }
 }
 
 int tail_tb(int J) { (void)J; return 32; }
@@ -438,7 +569,7 @@ int launch_head_backward(const HeadArgs& a, cudaStream_t s) {
   if (a.J > 64 || a.H > 64) return -2;
   tail_attrs();
   const int TB = tail_tb(a.J);
-  {
+  if (!a.fused_blocks) {                 // op path: separate tail kernel writes d1
     ProfScope ps(kProfHeadTail, s);
     if (a.y) k_head_tail<2><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
     else k_head_tail<1><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
