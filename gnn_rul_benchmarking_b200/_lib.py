@@ -62,6 +62,10 @@ class StgModelParams(C.Structure):
                 ("blk", StgModelBlock * MAX_BLOCKS), ("fc_w", C.c_void_p * 4), ("fc_b", C.c_void_p * 4)]
 
 
+class StgTcnParams(C.Structure):
+    _fields_ = [("conv1_w", C.c_void_p), ("bn1", StgBN), ("conv2_w", C.c_void_p), ("bn2", StgBN)]
+
+
 class StgDropout(C.Structure):
     _fields_ = [("keep", C.c_void_p), ("seed", C.c_uint64), ("step_dev", C.c_void_p)]
 
@@ -107,6 +111,11 @@ MODEL_SIGNATURES["stg_agg_forward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_void_p
                                                  C.c_void_p])
 MODEL_SIGNATURES["stg_agg_backward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
+MODEL_SIGNATURES["stg_tcn_forward"] = (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(StgTcnParams),
+                                                 C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p])
+MODEL_SIGNATURES["stg_tcn_backward"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  C.POINTER(StgTcnParams), C.POINTER(StgTcnParams), C.c_float,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p])
 SIGNATURES.update(MODEL_SIGNATURES)
 
 _lib = None

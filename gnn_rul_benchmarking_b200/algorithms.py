@@ -155,4 +155,24 @@ class FC_STGNN(Algorithm):
         return {"loss": self.step(X, y).item()}
 
 
-_ALGORITHMS = {"FC_STGNN": FC_STGNN}
+class ASTGCNN(Algorithm):
+    """algorithms.py:139-163: Adam(lr, weight_decay) + MSE around ASTGCNN_model (native TCN / adjacency /
+    Chebyshev aggregation, see astgcnn.py)."""
+
+    def __init__(self, configs, hparams, device):
+        super().__init__(configs)
+        from .astgcnn import ASTGCNN_model
+        self.model = ASTGCNN_model(**configs)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
+                                          weight_decay=hparams["weight_decay"], fused=None)
+        self.hparams = hparams
+
+    def update(self, X, y, epoch=None):
+        loss = self.mse(self.model(X), y)
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return {"loss": loss.item()}
+
+
+_ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN}

@@ -24,3 +24,9 @@ CONFIGS = {
 }
 # configs/hparams.py:133 train_params['FC_STGNN'] (identical for FD001-FD004 and N-CMAPSS)
 TRAIN_PARAMS = dict(num_epochs=81, batch_size=100, weight_decay=1e-4, learning_rate=1e-3)
+
+# ASTGCNN (BASELINE.json configs[2]): configs/hparams.py:38 (C-MAPSS, 14 sensors) and :202 (N-CMAPSS, 20 channels)
+ASTGCNN_CONFIGS = {
+    "CMAPSS": dict(num_nodes=14, time_length=50, encoder_out_dim=50, output_dim=64, K=3),
+    "NCMAPSS": dict(num_nodes=20, time_length=50, encoder_out_dim=50, output_dim=64, K=3),
+}

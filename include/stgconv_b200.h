@@ -238,6 +238,24 @@ int stg_agg_forward(int kind, const float* x_dev, const float* adj_dev, int64_t 
 int stg_agg_backward(int kind, const float* x_dev, const float* adj_dev, const float* dout_dev, int64_t G, int N,
                      int F, float* dx_dev, float* dadj_dev, void* stream);
 
+/* TemporalConvNet of the sibling models (primitive T1): two causal convolutions (dilation 1
+ * and 2, no bias, Chomp1d) each followed by BatchNorm1d + ReLU, with residual ReLUs
+ * (models/ASTGCNN/Model.py:72-146 kernel 6; models/ST_GCN/Model.py:99-173 kernel 2; ST_Conv, STAGNN).
+ * x / out [B, C, L]; C_in == C_out (downsample0/1 are None in every reference configuration).
+ * scratch_dev: 8*C doubles, written by the training forward and reused by the backward of the same batch. */
+typedef struct stg_tcn_params {
+  float* conv1_w;   /* conv_block1.0.weight [C,C,K] */
+  stg_bn bn1;       /* conv_block1.2.*      [C]     */
+  float* conv2_w;   /* conv_block2.0.weight [C,C,K] */
+  stg_bn bn2;       /* conv_block2.2.*      [C]     */
+} stg_tcn_params;
+int stg_tcn_forward(const float* x_dev, int B, int C, int L, int K, const stg_tcn_params* params, int training,
+                    float momentum, float eps, double* scratch_dev, float* out_dev, void* stream);
+/* grads: same struct, weight / bias pointers address gradient buffers (ACCUMULATED into). */
+int stg_tcn_backward(const float* x_dev, const float* dout_dev, int B, int C, int L, int K,
+                     const stg_tcn_params* params, const stg_tcn_params* grads, float eps, double* scratch_dev,
+                     float* dx_dev, void* stream);
+
 /* Evaluation metrics (utils.py:136-169, called every epoch from trainer.py:119-121): ACCUMULATES into
  * out4_dev (4 doubles, caller zeroes): [0] sum of Score_v1 terms, [1] sum of Score_v2 terms,
  * [2] sum |pred-real|, [3] sum (pred-real)^2.  Score_v2 average, MAE and RMSE follow as

@@ -27,3 +27,24 @@ for name, B in (("FD001", 256), ("FD002", 256), ("FD003", 256), ("FD004", 256), 
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / n
     print(f"{name:8s} B={B:5d}  {ms*1e3:8.1f} us/step  {B/ms*1e3:10.0f} windows/s  loss {float(loss):.4f}", flush=True)
+
+# ASTGCNN (BASELINE configs[2], N-CMAPSS shape, batch 512): native TCN / adjacency / Chebyshev aggregation
+import warnings
+from gnn_rul_benchmarking_b200.configs import ASTGCNN_CONFIGS
+for name, B in (("CMAPSS", 100), ("NCMAPSS", 512)):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        alg = get_algorithm_class("ASTGCNN")(ASTGCNN_CONFIGS[name], TRAIN_PARAMS, dev).to(dev)
+    alg.train()
+    N = ASTGCNN_CONFIGS[name]["num_nodes"]
+    X, y = torch.rand(B, N, 50, device=dev), torch.rand(B, 1, device=dev)
+    for _ in range(5):
+        alg.update(X, y, 1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 30
+    for _ in range(n):
+        alg.update(X, y, 1)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / n * 1e3
+    print(f"ASTGCNN {name:8s} B={B:5d}  {ms*1e3:8.1f} us/step  {B/ms*1e3:10.0f} windows/s", flush=True)

@@ -205,6 +205,31 @@ def aux_golden():
     layer_case("gcn_wide", GCNLayer(40, 100), (2, 32, 40), True)       # SAGCN-sized
     layer_case("cheb", ChebNet(50, 64, 3), (3, 14, 50), False)         # ASTGCNN FD004
     layer_case("cheb_small", ChebNet(5, 8, 3), (6, 20, 5), False)      # STGNN N-CMAPSS patch features
+    # ASTGCNN (BASELINE configs[2]): whole reference model, train + eval forward, all gradients, running stats
+    from models.ASTGCNN.Model import ASTGCNN_model                   # noqa: E402
+    for tag, cfg, bs in (("astgcnn_c", dict(num_nodes=14, time_length=50, encoder_out_dim=50, output_dim=64, K=3), 5),
+                         ("astgcnn_n", dict(num_nodes=20, time_length=50, encoder_out_dim=50, output_dim=64, K=3), 3)):
+        torch.manual_seed(2)
+        mdl = ASTGCNN_model(**cfg)
+        perturb_bn_(mdl, tg)
+        for k, v in mdl.state_dict().items():
+            out[f"{tag}/sd0/{k}"] = _np(v)
+        X = torch.rand(bs, cfg["num_nodes"], 50, generator=tg)
+        yt = torch.rand(bs, 1, generator=tg)
+        mdl.eval()
+        with torch.no_grad():
+            out[f"{tag}/y_eval"] = _np(mdl(X))
+        mdl.train()
+        pred = mdl(X)
+        loss = torch.nn.functional.mse_loss(pred, yt)
+        loss.backward()
+        out[f"{tag}/X"], out[f"{tag}/y"], out[f"{tag}/y_train"] = _np(X), _np(yt), _np(pred)
+        for k, p in mdl.named_parameters():
+            if p.grad is not None:
+                out[f"{tag}/grad/{k}"] = _np(p.grad)
+        for k, v in mdl.state_dict().items():
+            if "running_" in k or "num_batches" in k:
+                out[f"{tag}/sd1/{k}"] = _np(v)
     path = os.path.join(OUT, "aux_metrics_data.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
