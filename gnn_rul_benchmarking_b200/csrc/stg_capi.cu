@@ -71,7 +71,8 @@ const char* stg_version(void) { return "stgconv_b200 0.1 sm_100a"; }
 
 int stg_block_xmoments(const float* x_dev, int B, int T, int N, int C, double* xmom_dev, void* stream) {
   if (!x_dev || !xmom_dev || B < 1 || T < 1 || N < 1 || C < 1) return set_err(STG_ERR_INVALID, "bad argument");
-  launch_xmoments(x_dev, B, T, N, C, xmom_dev, (cudaStream_t)stream);
+  if (launch_xmoments(x_dev, B, T, N, C, xmom_dev, (cudaStream_t)stream))
+    return set_err(STG_ERR_CUDA, "k_xmoments launch failed");
   return check_cuda("stg_block_xmoments");
 }
 
@@ -87,7 +88,7 @@ int stg_block_forward(const float* x_dev, int B, int T, int N, int C, const stg_
   for (int z = 0; z < nblk; ++z)
     if (blk[z].out_bstride < (int64_t)a.b[z].L * N * a.b[z].H)
       return set_err(STG_ERR_INVALID, "block %d: out_bstride smaller than L*N*H", z);
-  launch_block_forward(a, p, (cudaStream_t)stream);
+  if (launch_block_forward(a, p, (cudaStream_t)stream)) return set_err(STG_ERR_CUDA, "block forward launch failed");
   return check_cuda("stg_block_forward");
 }
 
@@ -103,7 +104,7 @@ int stg_block_backward(const float* x_dev, int B, int T, int N, int C, const stg
   char err[256];
   rc = plan_blocks(a, p, err, sizeof(err));
   if (rc) return set_err(rc == -1 ? STG_ERR_INVALID : STG_ERR_UNSUPPORTED, "%s", err);
-  launch_block_backward(a, p, (cudaStream_t)stream);
+  if (launch_block_backward(a, p, (cudaStream_t)stream)) return set_err(STG_ERR_CUDA, "block backward launch failed");
   return check_cuda("stg_block_backward");
 }
 

@@ -520,8 +520,16 @@ void bwd1_launch(const HeadArgs& a, cudaStream_t s) {
   if (slices > a.B) slices = a.B;
   int bper = (a.B + slices - 1) / slices;
   if ((size_t)bper * a.J * 4 > 40 * 1024) bper = (int)(40 * 1024 / (a.J * 4));
+  if (a.fused_blocks && bper > 32) bper = 32;          // the in-kernel tail keeps ~(3J+2H) floats per sample
   slices = (a.B + bper - 1) / bper;
   const size_t sm_d1 = (size_t)((bper * a.J + 3) / 4) * 4 * 4;
+  static bool attr_done = false;                       // per instantiation: dynamic smem may exceed 48 KB
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_head_bwd1<JP, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_head_bwd1<JP, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_head_bwd1<JP, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
   if (a.fused_blocks) {
     // model path: the tail (fc2..fc4, loss, its backward) is recomputed per slice inside this kernel
     const size_t smt = sm_d1 + tail_slice_floats(a.J, a.H, bper) * 4;

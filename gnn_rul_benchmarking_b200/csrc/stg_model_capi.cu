@@ -226,18 +226,20 @@ int run_forward(Ctx& c, const stg_model_params& p, int training, float* pred, bo
                        (long long*)p.blk[0].bn1.num_batches_tracked, (long long*)p.blk[1].bn0.num_batches_tracked,
                        (long long*)p.blk[1].bn1.num_batches_tracked, (long long*)c.enc.seed_ptr};
   // one launch: clear the reduction scratch, tick num_batches_tracked + dropout counter, clear the loss
-  launch_zero(base + c.w.dbl, c.w.dbl_end - c.w.dbl, nbt, training ? 8 : 0, zero1, s);
-  launch_encoder_forward(c.enc, c.enc_smem_f, s);
+  int rc = launch_zero(base + c.w.dbl, c.w.dbl_end - c.w.dbl, nbt, training ? 8 : 0, zero1, s);
+  if (rc) return set_err(STG_ERR_CUDA, "k_zero launch failed");
+  if (launch_encoder_forward(c.enc, c.enc_smem_f, s)) return set_err(STG_ERR_CUDA, "encoder forward launch failed");
   if (training) {
     // block stats are cleared by the step's k_zero; tables come with the x-moments (one launch)
-    launch_xmoments_prep(c.blk, c.plan, (double*)(base + c.w.xmom), (unsigned*)(base + c.w.cnt), s);
+    if (launch_xmoments_prep(c.blk, c.plan, (double*)(base + c.w.xmom), (unsigned*)(base + c.w.cnt), s))
+      return set_err(STG_ERR_CUDA, "k_xmoments_prep launch failed");
     c.blk.prep_done = 1;
   }
-  launch_block_forward(c.blk, c.plan, s);
+  if (launch_block_forward(c.blk, c.plan, s)) return set_err(STG_ERR_CUDA, "block forward launch failed");
   HeadArgs hd = c.head;
   hd.pred = with_tail ? pred : nullptr;
   hd.y = nullptr; hd.dpred = nullptr;     // pred == nullptr: fc1 only, the backward tail follows
-  launch_head_forward(hd, s);
+  if (launch_head_forward(hd, s)) return set_err(STG_ERR_CUDA, "head forward launch failed");
   return check_cuda("stg_model forward");
 }
 
@@ -245,9 +247,9 @@ int run_backward(Ctx& c, const float* y, const float* dpred, float* pred, cudaSt
   HeadArgs hd = c.head;
   hd.y = y; hd.dpred = dpred; hd.pred = pred;
   // all backward sums were cleared by the forward's first kernel: ONE backward per training forward
-  launch_head_backward(hd, s);
-  launch_block_backward(c.blk, c.plan, s);
-  launch_encoder_backward(c.enc, c.enc_smem_b, s);
+  if (launch_head_backward(hd, s)) return set_err(STG_ERR_CUDA, "head backward launch failed");
+  if (launch_block_backward(c.blk, c.plan, s)) return set_err(STG_ERR_CUDA, "block backward launch failed");
+  if (launch_encoder_backward(c.enc, c.enc_smem_b, s)) return set_err(STG_ERR_CUDA, "encoder backward launch failed");
   return check_cuda("stg_model backward");
 }
 

@@ -31,7 +31,8 @@ class PinnedDropout(torch.nn.Module):
         self.keep, self.p = keep, p
 
 
-@pytest.mark.parametrize("name,bs", [("FD001", 5), ("FD002", 3), ("FD003", 2), ("FD004", 7), ("NCMAPSS", 3), ("S2", 2)])
+@pytest.mark.parametrize("name,bs", [("FD001", 5), ("FD002", 3), ("FD003", 2), ("FD004", 7), ("NCMAPSS", 3), ("S2", 2),
+                                     ("FD003", 70), ("FD004", 131), ("S2", 40)])     # batch sizes that change the launch plans
 def test_model_forward_backward_vs_oracle(name, bs):
     from gnn_rul_benchmarking_b200.fc_stgnn import FC_STGNN_RUL
     cfg = orc.CONFIGS[name]
