@@ -175,4 +175,17 @@ class ASTGCNN(Algorithm):
         return {"loss": loss.item()}
 
 
-_ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN}
+class ST_GCN(ASTGCNN):
+    """algorithms.py:465-491: same update rule around ST_GCN_model (native statistics / Pearson adjacency /
+    aggregation / TCN, see st_gcn.py)."""
+
+    def __init__(self, configs, hparams, device):
+        Algorithm.__init__(self, configs)
+        from .st_gcn import ST_GCN_model
+        self.model = ST_GCN_model(**configs)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
+                                          weight_decay=hparams["weight_decay"])
+        self.hparams = hparams
+
+
+_ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN, "ST_GCN": ST_GCN}

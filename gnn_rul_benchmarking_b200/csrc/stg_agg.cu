@@ -3,6 +3,7 @@
 // matmuls) are plain GEMMs and stay with the caller.
 //   STG_AGG_GCN    Y = D^-1/2 (A+I) D^-1/2 X,  D = rowsum(A+I)      SAGCN/Model.py:81-95, STMSGCN:34-49, RGCNU:7-21
 //   STG_AGG_CHEB3  T = [X, A X, 2 A (A X) - X]  (Chebyshev, raw A)   ASTGCNN/Model.py:212-228, STGNN:43-59, STNet:21-37
+//   STG_AGG_AX     Y = A X  (MPNN_mk with k = 1, primitive M1)       ST_GCN/Model.py:80-90, ST_Conv, HierCorrPool, LOGO
 // X [G,N,F], A [G,N,N] -> GCN: Y [G,N,F];  CHEB3: T [G,3,N,F].
 #include <math.h>
 
@@ -52,6 +53,16 @@ __global__ void __launch_bounds__(kAggThreads) k_agg_fwd(int kind, const float* 
       float acc = 0.f;
       for (int j = 0; j < N; ++j) acc = fmaf(As[i * N + j], t1[j * FP + c], acc);
       Yg[e] = sc[i] * acc;
+    }
+    return;
+  }
+  if (kind == STG_AGG_AX) {                                  // MPNN_mk, k = 1: plain A X
+    float* Yg = Y + g * N * F;
+    for (int e = tid; e < N * F; e += blockDim.x) {
+      const int i = e / F, c = e - i * F;
+      float acc = 0.f;
+      for (int j = 0; j < N; ++j) acc = fmaf(As[i * N + j], xs[j * FP + c], acc);
+      Yg[e] = acc;
     }
     return;
   }
@@ -128,6 +139,24 @@ __global__ void __launch_bounds__(kAggThreads) k_agg_bwd(int kind, const float* 
     }
     return;
   }
+  if (kind == STG_AGG_AX) {                                  // dX = A^T dY ; dA = dY X^T
+    const float* dYg = dY + g * N * F;
+    for (int e = tid; e < N * F; e += blockDim.x) b1[(e / F) * FP + e % F] = dYg[e];
+    __syncthreads();
+    for (int e = tid; e < N * F; e += blockDim.x) {
+      const int j = e / F, c = e - j * F;
+      float acc = 0.f;
+      for (int i = 0; i < N; ++i) acc = fmaf(As[i * N + j], b1[i * FP + c], acc);
+      dXg[e] = acc;
+    }
+    for (int e = tid; e < N * N; e += blockDim.x) {
+      const int i = e / N, j = e - i * N;
+      float d = 0.f;
+      for (int c = 0; c < F; ++c) d = fmaf(b1[i * FP + c], xs[j * FP + c], d);
+      dAg[e] = d;
+    }
+    return;
+  }
   // ---- CHEB3: dT [3][N][F];  dT1' = dT1 + 2 A^T dT2 ; dX = dT0 - dT2 + A^T dT1' ; dA = dT1' X^T + 2 dT2 T1^T
   const float* dTg = dY + g * 3 * N * F;
   for (int e = tid; e < N * F; e += blockDim.x) {
@@ -166,7 +195,7 @@ using namespace stg;
 
 static int agg_check(int kind, const void* x, const void* a, const void* y, long long G, int N, int F, bool bwd) {
   if (!x || !a || !y || G < 1 || N < 1 || F < 1) return set_err(STG_ERR_INVALID, "bad argument");
-  if (kind != STG_AGG_GCN && kind != STG_AGG_CHEB3) return set_err(STG_ERR_INVALID, "unknown aggregation kind %d", kind);
+  if (kind != STG_AGG_GCN && kind != STG_AGG_CHEB3 && kind != STG_AGG_AX) return set_err(STG_ERR_INVALID, "unknown aggregation kind %d", kind);
   if (agg_smem(N, F, bwd) > 200 * 1024)
     return set_err(STG_ERR_UNSUPPORTED, "graph of %d nodes x %d features does not fit the aggregation tile", N, F);
   if (!g_agg_attr) {

@@ -1,0 +1,56 @@
+// Hand-crafted per-patch statistics of the bearing models' parameter-free prefix:
+// segment_and_compute_features, models/ST_GCN/Model.py:7-52 -- for every patch (row of P samples):
+//   max, min, peak-to-peak, variance (unbiased), std (unbiased), mean, rms, mean |x|,
+//   skewness mean(((x-mean)/std)^3), excess kurtosis mean(((x-mean)/std)^4) - 3.
+// One warp per patch, two passes over the row held in registers / re-read from L1 (sm_100a).
+// No learnable parameter lies upstream, so there is no backward.
+#include <math.h>
+
+#include "../../include/stgconv_b200.h"
+#include "stg_common.cuh"
+
+namespace stg {
+namespace {
+__global__ void __launch_bounds__(256) k_patch_stats(const float* __restrict__ x, long long R, int P,
+                                                     float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float* xr = x + row * P;
+  float mx = -INFINITY, mn = INFINITY, s = 0.f, sq = 0.f, sa = 0.f;
+  for (int i = lane; i < P; i += 32) {
+    const float v = xr[i];
+    mx = fmaxf(mx, v); mn = fminf(mn, v);
+    s += v; sq = fmaf(v, v, sq); sa += fabsf(v);
+  }
+  mx = warp_max(mx);
+  mn = -warp_max(-mn);
+  s = warp_sum(s); sq = warp_sum(sq); sa = warp_sum(sa);
+  const float mean = s / (float)P;
+  float m2 = 0.f;
+  for (int i = lane; i < P; i += 32) { const float d = xr[i] - mean; m2 = fmaf(d, d, m2); }
+  m2 = warp_sum(m2);
+  const float var = m2 / (float)(P - 1), sd = sqrtf(var);       // torch.var / torch.std default: unbiased
+  float m3 = 0.f, m4 = 0.f;
+  for (int i = lane; i < P; i += 32) {
+    const float z = (xr[i] - mean) / sd, z2 = z * z;
+    m3 = fmaf(z2, z, m3); m4 = fmaf(z2, z2, m4);
+  }
+  m3 = warp_sum(m3); m4 = warp_sum(m4);
+  if (lane == 0) {
+    float* o = out + row * 10;
+    o[0] = mx; o[1] = mn; o[2] = mx - mn; o[3] = var; o[4] = sd; o[5] = mean;
+    o[6] = sqrtf(sq / (float)P); o[7] = sa / (float)P; o[8] = m3 / (float)P; o[9] = m4 / (float)P - 3.f;
+  }
+}
+}  // namespace
+}  // namespace stg
+
+using namespace stg;
+
+extern "C" int stg_patch_stats(const float* x_dev, int64_t R, int P, float* out_dev, void* stream) {
+  if (!x_dev || !out_dev || R < 1 || P < 2) return set_err(STG_ERR_INVALID, "bad argument (patches need >= 2 samples)");
+  const long long grid = (R + 7) / 8;
+  k_patch_stats<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x_dev, (long long)R, P, out_dev);
+  return check_cuda("stg_patch_stats");
+}

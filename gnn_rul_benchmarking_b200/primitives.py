@@ -67,7 +67,7 @@ def compute_adjacency_matrix(input: torch.Tensor, top_k: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------ M2 / M3
-AGG_GCN, AGG_CHEB3 = 0, 1
+AGG_GCN, AGG_CHEB3, AGG_AX = 0, 1, 2
 
 
 class _Aggregate(torch.autograd.Function):
@@ -77,7 +77,7 @@ class _Aggregate(torch.autograd.Function):
             raise RuntimeError("graph aggregation runs on the device (no CPU fallback)")
         G, N, F = x.shape
         xc, ac = x.contiguous(), adj.contiguous()
-        out = torch.empty((G, N, F) if kind == AGG_GCN else (G, 3, N, F), device=x.device, dtype=torch.float32)
+        out = torch.empty((G, 3, N, F) if kind == AGG_CHEB3 else (G, N, F), device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
             _lib.check(_lib.load().stg_agg_forward(kind, xc.data_ptr(), ac.data_ptr(), G, N, F, out.data_ptr(), _stream()),
                        "stg_agg_forward")
@@ -132,3 +132,35 @@ class ChebNet(torch.nn.Module):
     def forward(self, x, adj_matrix):
         T = cheb_terms(x, adj_matrix)                                  # [bs, 3, N, f]
         return torch.einsum("bknf,kfo->bno", T, self.filters)
+
+
+def graph_matmul(A: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """torch.bmm(A, X) of MPNN_mk.forward (k = 1; models/ST_GCN/Model.py:85-88): A [bs,N,N], X [bs,N,f]."""
+    return _Aggregate.apply(X, A, AGG_AX)
+
+
+class MPNN_mk(torch.nn.Module):
+    """models/ST_GCN/Model.py:74-90 (also ST_Conv, HierCorrPool, LOGO, AGCN_TF): leaky_relu(sum_k theta_k(A^k X)).
+    The reference only ever instantiates k = 1."""
+
+    def __init__(self, input_dimension, output_dimension, k):
+        super().__init__()
+        if k != 1:
+            raise NotImplementedError("the reference configurations use k = 1")
+        self.k = k
+        self.theta = torch.nn.ModuleList([torch.nn.Linear(input_dimension, output_dimension) for _ in range(k)])
+
+    def forward(self, X, A):
+        return torch.nn.functional.leaky_relu(self.theta[0](graph_matmul(A, X)))
+
+
+def segment_and_compute_features(data: torch.Tensor) -> torch.Tensor:
+    """models/ST_GCN/Model.py:7-37: data [rows, patch_size] -> [rows, 10] statistics (forward only)."""
+    if not data.is_cuda:
+        raise RuntimeError("patch statistics run on the device (no CPU fallback)")
+    x = data.detach().contiguous().float()
+    R, P = x.shape
+    out = torch.empty(R, 10, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().stg_patch_stats(x.data_ptr(), R, P, out.data_ptr(), _stream()), "stg_patch_stats")
+    return out

@@ -232,7 +232,7 @@ int stg_adj_backward(int kind, const float* x_dev, const float* adj_dev, const f
  *   STG_AGG_GCN    out [G,N,F]   = D^-1/2 (A+I) D^-1/2 X       models/SAGCN/Model.py:81-95, STMSGCN:34-49, RGCNU:7-21
  *   STG_AGG_CHEB3  out [G,3,N,F] = [X, A X, 2 A (A X) - X]     models/ASTGCNN/Model.py:212-228, STGNN:43-59
  * backward: dout (same shape as out) -> dx [G,N,F], dadj [G,N,N]. */
-enum { STG_AGG_GCN = 0, STG_AGG_CHEB3 = 1 };
+enum { STG_AGG_GCN = 0, STG_AGG_CHEB3 = 1, STG_AGG_AX = 2 /* out = A X: MPNN_mk k=1, models/ST_GCN/Model.py:80-90 */ };
 int stg_agg_forward(int kind, const float* x_dev, const float* adj_dev, int64_t G, int N, int F, float* out_dev,
                     void* stream);
 int stg_agg_backward(int kind, const float* x_dev, const float* adj_dev, const float* dout_dev, int64_t G, int N,
@@ -255,6 +255,11 @@ int stg_tcn_forward(const float* x_dev, int B, int C, int L, int K, const stg_tc
 int stg_tcn_backward(const float* x_dev, const float* dout_dev, int B, int C, int L, int K,
                      const stg_tcn_params* params, const stg_tcn_params* grads, float eps, double* scratch_dev,
                      float* dx_dev, void* stream);
+
+/* Per-patch statistics of the bearing models' parameter-free prefix: segment_and_compute_features
+ * (models/ST_GCN/Model.py:7-52).  x [R, P] -> out [R, 10] = max, min, ptp, var, std (unbiased), mean, rms,
+ * mean|x|, skewness, excess kurtosis.  Forward only (no parameter upstream). */
+int stg_patch_stats(const float* x_dev, int64_t R, int P, float* out_dev, void* stream);
 
 /* Evaluation metrics (utils.py:136-169, called every epoch from trainer.py:119-121): ACCUMULATES into
  * out4_dev (4 doubles, caller zeroes): [0] sum of Score_v1 terms, [1] sum of Score_v2 terms,

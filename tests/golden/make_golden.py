@@ -230,6 +230,36 @@ def aux_golden():
         for k, v in mdl.state_dict().items():
             if "running_" in k or "num_batches" in k:
                 out[f"{tag}/sd1/{k}"] = _np(v)
+    # ST_GCN (BASELINE configs[2]; PHM2012 hparams with dropout disabled so that train mode is reproducible)
+    from models.ST_GCN.Model import ST_GCN_model, segment_and_compute_features   # noqa: E402
+    xs_ = torch.rand(37, 64, generator=tg) * 2 - 0.7
+    out["stats/x"], out["stats/f"] = _np(xs_), _np(segment_and_compute_features(xs_))
+    for tag, cfg, bs in (("stgcn_40", dict(num_patch=40, patch_size=64, dropout=0.2), 4),
+                         ("stgcn_160", dict(num_patch=160, patch_size=16, dropout=0.2), 2)):
+        torch.manual_seed(4)
+        mdl = ST_GCN_model(**cfg)
+        perturb_bn_(mdl, tg)
+        for li, layer in enumerate(mdl.sg_tcn.layers):           # pin the dropout masks (train mode)
+            keep = (torch.rand(bs, 10, cfg["num_patch"], generator=tg) >= 0.2).float()
+            layer[2] = PinnedDropout(keep, 0.2)
+            out[f"{tag}/keep{li}"] = _np(keep)
+        for k, v in mdl.state_dict().items():
+            out[f"{tag}/sd0/{k}"] = _np(v)
+        X = torch.rand(bs, cfg["num_patch"] * cfg["patch_size"], generator=tg)
+        yt = torch.rand(bs, 1, generator=tg)
+        mdl.eval()
+        with torch.no_grad():
+            out[f"{tag}/y_eval"] = _np(mdl(X))
+        mdl.train()
+        pred = mdl(X)
+        torch.nn.functional.mse_loss(pred, yt).backward()
+        out[f"{tag}/X"], out[f"{tag}/y"], out[f"{tag}/y_train"] = _np(X), _np(yt), _np(pred)
+        for k, p in mdl.named_parameters():
+            if p.grad is not None:
+                out[f"{tag}/grad/{k}"] = _np(p.grad)
+        for k, v in mdl.state_dict().items():
+            if "running_" in k or "num_batches" in k:
+                out[f"{tag}/sd1/{k}"] = _np(v)
     path = os.path.join(OUT, "aux_metrics_data.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
