@@ -188,4 +188,28 @@ class ST_GCN(ASTGCNN):
         self.hparams = hparams
 
 
-_ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN, "ST_GCN": ST_GCN}
+class STGNN(ASTGCNN):
+    """reference algorithms.py class STGNN: same update rule around STGNN_model (stgnn.py)."""
+
+    def __init__(self, configs, hparams, device):
+        Algorithm.__init__(self, configs)
+        from .stgnn import STGNN_model
+        self.model = STGNN_model(**configs)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
+                                          weight_decay=hparams["weight_decay"])
+        self.hparams = hparams
+
+
+class STMSGCN(ASTGCNN):
+    """reference algorithms.py class STMSGCN: same update rule around STMSGCN_model (stgnn.py)."""
+
+    def __init__(self, configs, hparams, device):
+        Algorithm.__init__(self, configs)
+        from .stgnn import STMSGCN_model
+        self.model = STMSGCN_model(**configs)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
+                                          weight_decay=hparams["weight_decay"])
+        self.hparams = hparams
+
+
+_ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN, "ST_GCN": ST_GCN, "STGNN": STGNN, "STMSGCN": STMSGCN}

@@ -4,6 +4,7 @@
 //   STG_ADJ_COSINE    cosine similarity of the rows        HAGCN/Model.py:122-127, SAGCN:74-79
 //   STG_ADJ_GAUSS     exp(-||xi-xj||)                      ASTGCNN/Model.py:184-195 (after its Linear P)
 //   STG_ADJ_GAUSS2    exp(-||xi-xj||^2), top-k per row     STGNN/Model.py:8-25
+//   STG_ADJ_GRAM      x x^T (outer-product adjacency)      STMSGCN/Model.py:96
 // X [G, N, F] -> A [G, N, N].  The graph's rows are staged once in shared memory (pitch F+1), row norms /
 // means are warp-shuffle reductions, every (i,j) entry is one thread's dot product.  The backward uses
 // the closed forms (u = x/|x|: dx = (dU - (dU.u)u)/|x| with dU_i = sum_j (dA_ij + dA_ji) u_j;
@@ -58,10 +59,10 @@ __global__ void __launch_bounds__(kAdjThreads) k_adj_fwd(int kind, const float* 
     const int i = e / N, j = e - i * N;
     const float *xi = xs + i * FP, *xj = xs + j * FP;
     float v;
-    if (cosine_like) {
+    if (cosine_like || kind == STG_ADJ_GRAM) {
       float d = 0.f;
       for (int c = 0; c < F; ++c) d = fmaf(xi[c], xj[c], d);
-      v = d * rn[i] * rn[j];
+      v = kind == STG_ADJ_GRAM ? d : d * rn[i] * rn[j];
     } else {
       float d2 = 0.f;
       for (int c = 0; c < F; ++c) { const float t = xi[c] - xj[c]; d2 = fmaf(t, t, d2); }
@@ -102,8 +103,9 @@ __global__ void __launch_bounds__(kAdjThreads) k_adj_bwd(int kind, const float* 
   adj_stage(X + g * N * F, N, F, FP, kind == STG_ADJ_PCC, cosine_like, xs, rn);
   const float* dAg = dA + g * N * N;
   const float* Ag = A + g * N * N;
-  if (cosine_like) {
-    for (int i = tid; i < N * F; i += blockDim.x) xs[(i / F) * FP + (i % F)] *= rn[i / F];     // u = x/|x|
+  if (cosine_like || kind == STG_ADJ_GRAM) {
+    if (cosine_like)
+      for (int i = tid; i < N * F; i += blockDim.x) xs[(i / F) * FP + (i % F)] *= rn[i / F];   // u = x/|x|
     for (int e = tid; e < N * N; e += blockDim.x) {
       const int i = e / N, j = e - i * N;
       Wg[e] = dAg[e] + dAg[j * N + i];
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(kAdjThreads) k_adj_bwd(int kind, const float* 
   for (int e = tid; e < N * F; e += blockDim.x) {
     const int i = e / F, c = e - i * F;
     float acc = 0.f;
-    if (cosine_like) {
+    if (cosine_like || kind == STG_ADJ_GRAM) {
       for (int j = 0; j < N; ++j) acc = fmaf(Wg[i * N + j], xs[j * FP + c], acc);
     } else {
       const float xi = xs[i * FP + c];
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kAdjThreads) k_adj_bwd(int kind, const float* 
   }
   __syncthreads();
   float* dXg = dX + g * N * F;
-  if (!cosine_like) {
+  if (!cosine_like) {                                  // distance kinds and GRAM: dX = dU
     for (int e = tid; e < N * F; e += blockDim.x) dXg[e] = dU[(e / F) * FP + (e % F)];
     return;
   }
@@ -177,7 +179,7 @@ void adj_attrs() {
 }
 int adj_check(int kind, const void* a, const void* b, long long G, int N, int F, bool bwd) {
   if (!a || !b || G < 1 || N < 1 || F < 1) return set_err(STG_ERR_INVALID, "bad argument");
-  if (kind < STG_ADJ_PCC || kind > STG_ADJ_GAUSS2) return set_err(STG_ERR_INVALID, "unknown adjacency kind %d", kind);
+  if (kind < STG_ADJ_PCC || kind > STG_ADJ_GRAM) return set_err(STG_ERR_INVALID, "unknown adjacency kind %d", kind);
   if (adj_smem(N, F, bwd) > 200 * 1024)
     return set_err(STG_ERR_UNSUPPORTED, "graph of %d nodes x %d features does not fit shared memory", N, F);
   return STG_OK;

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-ADJ_PCC, ADJ_COSINE, ADJ_GAUSS, ADJ_GAUSS2 = 0, 1, 2, 3
+ADJ_PCC, ADJ_COSINE, ADJ_GAUSS, ADJ_GAUSS2, ADJ_GRAM = 0, 1, 2, 3, 4
 
 
 def _stream():
@@ -59,6 +59,11 @@ def cosine_distance(matrix1: torch.Tensor) -> torch.Tensor:
 def gaussian_adjacency(PX: torch.Tensor) -> torch.Tensor:
     """exp(-cdist(PX, PX, p=2)) of models/ASTGCNN/Model.py:193-194 (apply the layer's Linear P first)."""
     return _Adjacency.apply(PX, ADJ_GAUSS, 0)
+
+
+def gram_adjacency(x: torch.Tensor) -> torch.Tensor:
+    """torch.bmm(x, x^T) of models/STMSGCN/Model.py:96: [G, N, f] -> [G, N, N]."""
+    return _Adjacency.apply(x, ADJ_GRAM, 0)
 
 
 def compute_adjacency_matrix(input: torch.Tensor, top_k: int) -> torch.Tensor:

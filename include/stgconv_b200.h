@@ -221,7 +221,8 @@ int stg_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, f
  *   STG_ADJ_GAUSS2  exp(-cdist^2), top_k per row  models/STGNN/Model.py:8-25 (top_k <= 0 or >= N: dense)
  * mask_dev (optional, GAUSS2): 0/1 bytes of the kept entries.  The backward takes the forward's adj
  * (masked entries are zero and carry no gradient). */
-enum { STG_ADJ_PCC = 0, STG_ADJ_COSINE = 1, STG_ADJ_GAUSS = 2, STG_ADJ_GAUSS2 = 3 };
+enum { STG_ADJ_PCC = 0, STG_ADJ_COSINE = 1, STG_ADJ_GAUSS = 2, STG_ADJ_GAUSS2 = 3,
+       STG_ADJ_GRAM = 4 /* x x^T, models/STMSGCN/Model.py:96 */ };
 int stg_adj_forward(int kind, const float* x_dev, int64_t G, int N, int F, int top_k, float* adj_dev,
                     unsigned char* mask_dev, void* stream);
 int stg_adj_backward(int kind, const float* x_dev, const float* adj_dev, const float* dadj_dev, int64_t G, int N,

@@ -260,6 +260,28 @@ def aux_golden():
         for k, v in mdl.state_dict().items():
             if "running_" in k or "num_batches" in k:
                 out[f"{tag}/sd1/{k}"] = _np(v)
+    # STGNN (FD004 / N-CMAPSS hparams) and STMSGCN (PHM2012 hparams): whole reference models
+    from models.STGNN.Model import STGNN_model                       # noqa: E402
+    from models.STMSGCN.Model import STMSGCN_model                   # noqa: E402
+    cases = (("stgnn_fd4", STGNN_model, dict(patch_size=50, num_patch=1, num_nodes=14, hidden_dim=64, K=3, top_k=10), (4, 14, 50)),
+             ("stgnn_nc", STGNN_model, dict(patch_size=5, num_patch=10, num_nodes=20, hidden_dim=64, K=3, top_k=10), (3, 20, 50)),
+             ("stmsgcn", STMSGCN_model, dict(num_patch=40, patch_size=64, interval=4, band_width=10,
+                                             gcn_dims=[16, 64, 16, 1], gru_hidden_dim=8), (3, 2560)))
+    for tag, cls, cfg, xshape in cases:
+        torch.manual_seed(6)
+        mdl = cls(**cfg)
+        for k, v in mdl.state_dict().items():
+            out[f"{tag}/sd0/{k}"] = _np(v)
+        X = torch.rand(*xshape, generator=tg)
+        yt = torch.rand(xshape[0], 1, generator=tg)
+        mdl.train()
+        pred = mdl(X)
+        torch.nn.functional.mse_loss(pred, yt).backward()
+        assert torch.isfinite(pred).all(), tag
+        out[f"{tag}/X"], out[f"{tag}/y"], out[f"{tag}/y_train"] = _np(X), _np(yt), _np(pred)
+        for k, p in mdl.named_parameters():
+            if p.grad is not None:
+                out[f"{tag}/grad/{k}"] = _np(p.grad)
     path = os.path.join(OUT, "aux_metrics_data.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
