@@ -1,60 +1,106 @@
-// Patch encoder + positional encoding of FC_STGNN_RUL, forward and backward (sm_100a).
+// Patch encoder + positional encoding of FC_STGNN_RUL, forward and backward (sm_100a), any dimensions.
 //   Feature_extractor_1DCNN_RUL (Model_Base.py:12-41), nonlin_map2 (Model.py:18-22,55-59),
 //   PositionalEncoding + Dropout (Model_Base.py:111-134, Model.py:62-68).
 //
-// One thread owns one row r = (b,t,n) (a patch of P samples of one sensor).  Everything a row needs
-// is recomputed from X in every phase (X is 4*N*L bytes per window -- the smallest tensor on the
-// path), so nothing but the BatchNorm moments crosses a phase boundary:
+// A row r = (b,t,n) is a patch of P samples of one sensor.  A CTA works on a tile of TR rows held in
+// shared memory as [feature][row] columns (odd pitch), and every stage -- conv1, conv2, the linear map,
+// their transposes and the weight-gradient outer products -- is spread over all 256 threads as
+// (feature, row) work items, the long contraction of the linear map additionally split over lanes.  So a
+// set with few, wide rows (FD001: 7168 rows x 864 conv2 features at batch 256) keeps every thread
+// busy, as does one with many narrow rows.  Everything a row needs is recomputed from X in every phase (X is
+// 4*N*L bytes per window -- the smallest tensor on the path), so nothing but the BatchNorm moments
+// crosses a phase boundary:
 //   training forward : F1 conv1 moments -> F2 conv2 moments -> F3 linear moments -> F4 write h
 //   eval forward     : F4 only (running statistics)
 //   backward         : B1 BN3 sums -> B2 dW3, db3, BN2 sums -> B3 dW2, BN1 sums -> B4 dW1
-// Per-row activations live in shared memory as [feature][row] columns (conflict-free for the
-// row-owner; odd row pitch makes the weight-gradient outer products conflict-free too), so all
-// dimensions are runtime values: every FC_STGNN hyper-parameter set of configs/hparams.py runs.
+// All dimensions are runtime values and TR is chosen per phase from what that phase keeps in shared
+// memory: every FC_STGNN hyper-parameter set of configs/hparams.py runs.  The sets with register-sized rows
+// (FD002/FD003/FD004/S2) take the compile-time path in stg_encoder_fast.cu instead.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "stg_model.cuh"
 
 namespace stg {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024;       // one CTA per SM (shared-memory bound): 32 warps hide the LDS->FMA chains
+constexpr int kWarps = kThreads / 32;
 constexpr size_t kSmemCap = 200 * 1024;
+constexpr int kMinTR = 4;
 
 struct Lay {          // offsets in floats from the dynamic smem base
-  int W1, W2, W3, b3, coef, q, pe, accW, sacc, xs, c1, c2, z, d2, d1, total;
+  int W1, W2, W3, b3, coef, q, pe, accW, sacc, meta, xs, c1, a1, c2, z, z2, d2, d1, total;
   int TRP;
 };
 
 __host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 
-__host__ __device__ inline Lay make_lay(const EncArgs& a, bool bwd) {
+__host__ __device__ inline int enc_npairs(const EncArgs& a, int ph) {
+  return ph == 5 ? a.C * a.EL2 + a.C : ph == 6 ? a.E * a.EH * a.K : ph == 7 ? a.EH * a.K : 0;
+}
+
+// What phase `ph` computes / keeps in shared memory.  In training the raw conv2 / linear outputs and the
+// masked gradients dn2 / dn1 stay in the workspace between phases (a.c2raw ...), so each heavy stage runs
+// once per step; in eval (one phase, running statistics) everything is computed in place.
+struct Use { bool x, a1, conv2, c2, lin, z, z2, d2, d1, W2, W3; };
+
+__host__ __device__ inline bool enc_kept(const EncArgs& a) { return a.training && a.c2raw != nullptr; }
+
+__host__ __device__ inline Use enc_use(const EncArgs& a, int ph) {
+  const bool k = enc_kept(a);
+  Use u;
+  u.x = !k || ph <= 1 || ph >= 6;                       // x and conv1 (cheap: always recomputed where needed)
+  u.a1 = k ? (ph == 1 || ph == 6) : ph >= 1;
+  u.conv2 = k ? ph == 1 : ph >= 1;                      // compute conv2 here
+  u.c2 = u.conv2 || (k && (ph == 2 || ph == 5 || ph == 6));     // tile holds conv2 (computed or loaded)
+  u.lin = k ? ph == 2 : ph >= 2;                        // compute the linear map here
+  u.z = u.lin || (k && ph >= 3 && ph <= 5);
+  u.z2 = k ? (ph == 4 || ph == 5) : ph >= 4;            // dz3 and the linear map's transpose happen here
+  u.d2 = k ? (ph == 5 || ph == 6) : ph >= 5;
+  u.d1 = ph >= 6;
+  u.W2 = u.conv2 || (u.d2 && ph >= 6);
+  u.W3 = u.lin || (u.z2 && ph >= 5);
+  return u;
+}
+
+__host__ __device__ inline Lay make_lay(const EncArgs& a, int ph) {
+  const Use u = enc_use(a, ph);
   Lay l;
   const int TRP = a.TR + 1;
   l.TRP = TRP;
   int o = 0;
   l.W1 = o; o += a.EH * a.K;
-  l.W2 = o; o += a.E * a.EH * a.K;
-  l.W3 = o; o += a.C * a.EL2;
+  l.W2 = o; o += u.W2 ? a.E * a.EH * a.K : 0;
+  l.W3 = o; o += u.W3 ? a.C * a.EL2 : 0;
   l.b3 = o; o += a.C;
   l.coef = o; o += 4 * (a.EH + a.E + a.C);       // per BN: A, Cc, mu, r
   l.q = o; o += 2 * (a.EH + a.E + a.C);          // per BN: backward means
-  l.pe = o; o += a.T * a.C;
-  l.accW = o; o += imax(imax(a.EH * a.K, a.E * a.EH * a.K), a.C * a.EL2 + a.C);
+  l.pe = o; o += ph == 3 ? a.T * a.C : 0;
+  l.accW = o; o += enc_npairs(a, ph);
   o = (o + 1) & ~1;
   l.sacc = o; o += 2 * 2 * imax(imax(a.EH, a.E), a.C);   // doubles
-  l.xs = o; o += a.P * TRP;
-  l.c1 = o; o += a.EH * a.L1 * TRP;
-  l.c2 = o; o += a.EL2 * TRP;
-  l.z = o; o += a.C * TRP;
-  l.d2 = o; l.d1 = o;
-  if (bwd) {
-    o += a.EL2 * TRP;
-    l.d1 = o; o += a.EH * a.L1 * TRP;
-  }
+  l.meta = o; o += 2 * a.TR;                     // per row: (b*N+n)*T+t, t
+  l.xs = o; o += u.x ? a.P * TRP : 0;
+  l.c1 = o; o += u.x ? a.EH * a.L1 * TRP : 0;    // raw conv1
+  l.a1 = o; o += u.a1 ? a.EH * a.L1 * TRP : 0;   // relu(BN1(conv1))
+  l.c2 = o; o += u.c2 ? a.EL2 * TRP : 0;         // raw conv2 (forward phases: relu(BN2) in place)
+  l.z = o; o += u.z ? a.C * TRP : 0;             // raw linear, then dz3
+  l.z2 = o; o += u.z2 ? a.C * TRP : 0;           // dropout'(dh)
+  l.d2 = o; o += u.d2 ? a.EL2 * TRP : 0;         // relu(BN2(conv2)), then dn2, then dc2
+  l.d1 = o; o += u.d1 ? a.EH * a.L1 * TRP : 0;   // dn1, then dc1
   l.total = o;
   return l;
+}
+
+inline int tile_rows_for(const EncArgs& a, int ph) {
+  EncArgs b = a;
+  for (int tr = 256; tr >= kMinTR; tr >>= 1) {
+    b.TR = tr;
+    if ((size_t)make_lay(b, ph).total * 4 <= kSmemCap) return tr;
+  }
+  return 0;
 }
 
 STG_DEVINL float keep_scale(const EncArgs& a, size_t idx) {
@@ -98,27 +144,46 @@ STG_DEVINL void bn_coefs(float* dst, int n, const double* stats, double count, c
   }
 }
 
-STG_DEVINL void stat_add(double* sacc, int idx, float v) {
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[idx], (double)v);
+// sums over one tile of f(ch, i) -> (u, v) for i in [0, cnt), one warp per channel (fixed owner: no atomics)
+template <typename Fn>
+STG_DEVINL void chan_stats(double* sacc, int nch, int cnt, Fn f) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int ch = warp; ch < nch; ch += kWarps) {
+    float s = 0.f, ss = 0.f;
+    for (int i = lane; i < cnt; i += 32) {
+      float u, v;
+      f(ch, i, u, v);
+      s += u;
+      ss += v;
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      sacc[ch] += (double)s;
+      sacc[nch + ch] += (double)ss;
+    }
+  }
 }
 
-// accW[pair] += sum over the tile's rows of f(pair, row); npairs small -> rows are sliced over threads.
-template <typename Fn>
-STG_DEVINL void pair_reduce(float* accW, int npairs, int TR, Fn f) {
+// accW[pair] += sum over the tile's rows of mk(pair)(row): the pair is decoded once, outside the row loop.
+// Few pairs -> the rows are sliced over threads (shared-memory atomics); many -> each thread owns its pairs.
+template <typename Mk>
+STG_DEVINL void pair_reduce(float* accW, int npairs, int TR, Mk mk) {
   const int tid = threadIdx.x;
   if (npairs <= kThreads / 2) {
     const int slices = kThreads / npairs;
     if (tid < npairs * slices) {
       const int pair = tid % npairs, sl = tid / npairs;
+      const auto f = mk(pair);
       float acc = 0.f;
-      for (int r = sl; r < TR; r += slices) acc += f(pair, r);
+      for (int r = sl; r < TR; r += slices) acc += f(r);
       atomicAdd(&accW[pair], acc);
     }
   } else {
     for (int pair = tid; pair < npairs; pair += kThreads) {
+      const auto f = mk(pair);
       float acc = 0.f;
-      for (int r = 0; r < TR; ++r) acc += f(pair, r);
+      for (int r = 0; r < TR; ++r) acc += f(r);
       accW[pair] += acc;
     }
   }
@@ -129,15 +194,20 @@ template <int PH>
 __global__ void __launch_bounds__(kThreads) k_encoder(const EncArgs a) {
   extern __shared__ __align__(16) float sm[];
   constexpr bool BWD = PH >= 4;
-  const Lay l = make_lay(a, BWD);
+  const Lay l = make_lay(a, PH);
   const int TRP = l.TRP, TR = a.TR, tid = threadIdx.x;
+  const int lg = 31 - __clz(TR), rmask = TR - 1;            // TR is a power of two
   const int EH = a.EH, E = a.E, C = a.C, K = a.K, P = a.P, L1 = a.L1, L2 = a.L2, EL2 = a.EL2, N = a.N, T = a.T;
+  const int NL1 = EH * L1;
   float *W1 = sm + l.W1, *W2 = sm + l.W2, *W3 = sm + l.W3, *b3 = sm + l.b3;
   float *cf1 = sm + l.coef, *cf2 = cf1 + 4 * EH, *cf3 = cf2 + 4 * E;
   float *q1 = sm + l.q, *q2 = q1 + 2 * EH, *q3 = q2 + 2 * E;
   float *pe = sm + l.pe, *accW = sm + l.accW;
   double* sacc = reinterpret_cast<double*>(sm + l.sacc);
-  float *xs = sm + l.xs, *c1 = sm + l.c1, *c2 = sm + l.c2, *zz = sm + l.z, *d2 = sm + l.d2, *d1 = sm + l.d1;
+  int *rowk = reinterpret_cast<int*>(sm + l.meta), *rowt = rowk + TR;
+  float *xs = sm + l.xs, *c1 = sm + l.c1, *a1 = sm + l.a1, *c2 = sm + l.c2, *zz = sm + l.z, *z2 = sm + l.z2;
+  float *d2 = sm + l.d2, *d1 = sm + l.d1;
+  float* a2 = PH >= 5 ? d2 : c2;                            // where relu(BN2(conv2)) is materialised
 
   const double cnt1 = (double)a.R * L1, cnt2 = (double)a.R * L2, cnt3 = (double)a.R;
   const double* S1 = a.st;                     // forward moments
@@ -148,12 +218,12 @@ __global__ void __launch_bounds__(kThreads) k_encoder(const EncArgs a) {
   double* Bq1 = Bq2 + 2 * E;
 
   // ---------------- prologue: weights, BN coefficients ----------------
+  const Use u = enc_use(a, PH);
+  const bool kept = enc_kept(a);
   for (int i = tid; i < EH * K; i += kThreads) W1[i] = a.W1[i];
-  if (PH >= 1) for (int i = tid; i < E * EH * K; i += kThreads) W2[i] = a.W2[i];
-  if (PH >= 2) {
-    for (int i = tid; i < C * EL2; i += kThreads) W3[i] = a.W3[i];
-    for (int i = tid; i < C; i += kThreads) b3[i] = a.b3[i];
-  }
+  if (u.W2) for (int i = tid; i < E * EH * K; i += kThreads) W2[i] = a.W2[i];
+  if (u.W3) for (int i = tid; i < C * EL2; i += kThreads) W3[i] = a.W3[i];
+  if (PH >= 2) for (int i = tid; i < C; i += kThreads) b3[i] = a.b3[i];
   const bool first = blockIdx.x == 0;
   const bool tr = a.training != 0;
   if (PH >= 1) bn_coefs(cf1, EH, tr ? S1 : nullptr, cnt1, a.g1, a.be1, a.rm1, a.rv1, a.eps, a.momentum, tr && first && PH == 1);
@@ -175,8 +245,7 @@ __global__ void __launch_bounds__(kThreads) k_encoder(const EncArgs a) {
     q1[EH + c] = (float)(Bq1[EH + c] / cnt1);
     if (first) { a.dbe1[c] += (float)Bq1[c]; a.dg1[c] += (float)Bq1[EH + c]; }
   }
-  constexpr int kNPairsNone = 0;
-  const int npairs = PH == 5 ? C * EL2 + C : PH == 6 ? E * EH * K : PH == 7 ? EH * K : kNPairsNone;
+  const int npairs = enc_npairs(a, PH);
   for (int i = tid; i < npairs; i += kThreads) accW[i] = 0.f;
   const int nstat = PH == 0 ? EH : PH == 1 ? E : PH == 2 ? C : PH == 4 ? C : PH == 5 ? E : PH == 6 ? EH : 0;
   for (int i = tid; i < 2 * nstat; i += kThreads) sacc[i] = 0.0;
@@ -186,242 +255,319 @@ __global__ void __launch_bounds__(kThreads) k_encoder(const EncArgs a) {
   const float *A2 = cf2, *C2 = cf2 + E, *mu2 = cf2 + 2 * E, *r2 = cf2 + 3 * E;
   const float *A3 = cf3, *C3 = cf3 + C, *mu3 = cf3 + 2 * C, *r3 = cf3 + 3 * C;
 
+  // linear map: (4 outputs, row) items, the EL2-long contraction split over ks lanes of a warp
+  const int ncg = (C + 3) >> 2, nitems = ncg * TR;
+  int ks = 1;
+  while (ks < 32 && nitems * ks * 2 <= kThreads) ks <<= 1;
+  const int ipp = kThreads / ks, slice = tid & (ks - 1), islot = tid / ks;
+  const int neg = (E + 3) >> 2, nkg = (EL2 + 3) >> 2, nhg = (EH + 3) >> 2;      // 4-wide output groups
+
+  // tile <-> workspace ([row][feature], feature fastest: coalesced; odd smem pitch: conflict-free)
+  auto tile_load = [&](float* dst, const float* src, int F, int r0, int rows) {
+    for (int o = tid; o < F * TR; o += kThreads) {
+      const int rr = o / F, f = o - rr * F;
+      dst[f * TRP + rr] = rr < rows ? src[(size_t)(r0 + rr) * F + f] : 0.f;
+    }
+  };
+  auto tile_store = [&](float* dst, const float* src, int F, int r0, int rows) {
+    for (int o = tid; o < F * rows; o += kThreads) {
+      const int rr = o / F, f = o - rr * F;
+      dst[(size_t)(r0 + rr) * F + f] = src[f * TRP + rr];
+    }
+  };
+
   const int ntiles = (a.R + TR - 1) / TR;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int r = tile * TR + tid;
-    const bool act = tid < TR && r < a.R;
-    int n = 0, t = 0, b = 0;
-    if (act) {
-      n = r % N;
-      const int bt = r / N;
-      t = bt % T;
-      b = bt / T;
-      // ---- x, conv1 (raw, pre-BN) ----
-      const float* xp = a.X + ((size_t)(b * N + n) * T + t) * P;
-      for (int i = 0; i < P; ++i) xs[i * TRP + tid] = xp[i];
-      for (int ch = 0; ch < EH; ++ch)
-        for (int p = 0; p < L1; ++p) {
-          float acc = 0.f;
-          for (int j = 0; j < K; ++j) {
-            const int q = p + j - a.pad1;
-            if (q >= 0 && q < P) acc = fmaf(W1[ch * K + j], xs[q * TRP + tid], acc);
-          }
-          c1[(ch * L1 + p) * TRP + tid] = acc;
+    const int r0 = tile * TR;
+    const int rows = min(TR, a.R - r0);
+    __syncthreads();                                          // the previous tile is fully consumed
+    if (tid < TR) {
+      int kx = 0, t = 0;
+      if (tid < rows) {
+        const int r = r0 + tid, n = r % N, bt = r / N;
+        t = bt % T;
+        kx = ((bt / T) * N + n) * T + t;
+      }
+      rowk[tid] = kx;
+      rowt[tid] = t;
+    }
+    __syncthreads();
+    if (u.x) {
+      // ---- x (zero rows past the end) ----
+      for (int o = tid; o < P * TR; o += kThreads) {
+        const int rr = o / P, p = o - rr * P;
+        xs[p * TRP + rr] = rr < rows ? a.X[(size_t)rowk[rr] * P + p] : 0.f;
+      }
+      __syncthreads();
+      // ---- conv1 (raw, pre-BN) and a1 = relu(BN1(c1)) ----
+      for (int o = tid; o < NL1 * TR; o += kThreads) {
+        const int rr = o & rmask, f = o >> lg, ch = f / L1, p = f - ch * L1;
+        float acc = 0.f;
+        for (int j = 0; j < K; ++j) {
+          const int q = p + j - a.pad1;
+          if (q >= 0 && q < P) acc = fmaf(W1[ch * K + j], xs[q * TRP + rr], acc);
         }
+        c1[f * TRP + rr] = acc;
+        if (u.a1) a1[f * TRP + rr] = fmaxf(fmaf(A1[ch], acc, C1[ch]), 0.f);
+      }
+      __syncthreads();
     }
     if (PH == 0) {
-      for (int ch = 0; ch < EH; ++ch) {
-        float s = 0.f, ss = 0.f;
-        if (act)
-          for (int p = 0; p < L1; ++p) {
-            const float v = c1[(ch * L1 + p) * TRP + tid];
-            s += v;
-            ss = fmaf(v, v, ss);
-          }
-        stat_add(sacc, ch, s);
-        stat_add(sacc, EH + ch, ss);
-      }
+      chan_stats(sacc, EH, L1 * TR, [&](int ch, int i, float& su, float& sv) {
+        const int rr = i & rmask, p = i >> lg;
+        const float x = rr < rows ? c1[(ch * L1 + p) * TRP + rr] : 0.f;
+        su = x;
+        sv = x * x;
+      });
       continue;
     }
-    // ---- conv2 (raw) on a1 = relu(BN1(c1)) ----
-    if (act)
-      for (int e = 0; e < E; ++e)
-        for (int p = 0; p < L2; ++p) {
-          float acc = 0.f;
-          for (int ch = 0; ch < EH; ++ch) {
-            const float Ac = A1[ch], Cc = C1[ch];
-            for (int j = 0; j < K; ++j) {
-              const int q = p + j - 1;
-              if (q >= 0 && q < L1) {
-                const float av = fmaxf(fmaf(Ac, c1[(ch * L1 + q) * TRP + tid], Cc), 0.f);
-                acc = fmaf(W2[(e * EH + ch) * K + j], av, acc);
-              }
+    if (u.conv2) {
+      // ---- conv2 (raw): items (4 output channels, position, row) share each a1 load ----
+      for (int o = tid; o < neg * L2 * TR; o += kThreads) {
+        const int rr = o & rmask, f = o >> lg, eg = f / L2, p = f - eg * L2, e0 = eg << 2;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ch = 0; ch < EH; ++ch)
+          for (int j = 0; j < K; ++j) {
+            const int q = p + j - 1;
+            if (q >= 0 && q < L1) {
+              const float av = a1[(ch * L1 + q) * TRP + rr];
+              const float* w = W2 + (e0 * EH + ch) * K + j;
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                if (e0 + v < E) acc[v] = fmaf(w[v * EH * K], av, acc[v]);
             }
           }
-          c2[(e * L2 + p) * TRP + tid] = acc;
-        }
-    if (PH == 1) {
-      for (int e = 0; e < E; ++e) {
-        float s = 0.f, ss = 0.f;
-        if (act)
-          for (int p = 0; p < L2; ++p) {
-            const float v = c2[(e * L2 + p) * TRP + tid];
-            s += v;
-            ss = fmaf(v, v, ss);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (e0 + v < E) {
+            const int k = (e0 + v) * L2 + p;
+            c2[k * TRP + rr] = acc[v];
+            if (PH >= 2) a2[k * TRP + rr] = fmaxf(fmaf(A2[e0 + v], acc[v], C2[e0 + v]), 0.f);   // own element
           }
-        stat_add(sacc, e, s);
-        stat_add(sacc, E + e, ss);
       }
+      __syncthreads();
+      if (PH == 1 && kept) tile_store(a.c2raw, c2, EL2, r0, rows);
+    } else if (u.c2) {
+      // ---- raw conv2 from the workspace; a2 = relu(BN2) beside it (B2) or in its place (F3) ----
+      for (int o = tid; o < EL2 * TR; o += kThreads) {
+        const int rr = o / EL2, k = o - rr * EL2, e = k / L2;
+        const float v = rr < rows ? a.c2raw[(size_t)(r0 + rr) * EL2 + k] : 0.f;
+        c2[k * TRP + rr] = v;
+        if (PH == 2 || PH == 5) a2[k * TRP + rr] = fmaxf(fmaf(A2[e], v, C2[e]), 0.f);
+      }
+      __syncthreads();
+    }
+    if (PH == 1) {
+      chan_stats(sacc, E, L2 * TR, [&](int e, int i, float& su, float& sv) {
+        const int rr = i & rmask, p = i >> lg;
+        const float x = rr < rows ? c2[(e * L2 + p) * TRP + rr] : 0.f;
+        su = x;
+        sv = x * x;
+      });
       continue;
     }
-    // ---- linear (raw z3) on a2 = relu(BN2(c2)) ----
-    if (act)
-      for (int cb = 0; cb < C; cb += 4) {
-        float acc[4];
+    if (u.lin) {
+      // ---- linear (raw z3) on a2 ----
+      for (int base = 0; base < nitems; base += ipp) {
+        const int it = base + islot;
+        const bool valid = it < nitems;
+        const int rr = it & rmask, cb = (it >> lg) << 2;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (valid)
+          for (int k = slice; k < EL2; k += ks) {
+            const float av = a2[k * TRP + rr];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = (cb + u < C) ? b3[cb + u] : 0.f;
-        for (int k = 0; k < EL2; ++k) {
-          const int e = k / L2;
-          const float av = fmaxf(fmaf(A2[e], c2[k * TRP + tid], C2[e]), 0.f);
+            for (int v = 0; v < 4; ++v)
+              if (cb + v < C) acc[v] = fmaf(W3[(cb + v) * EL2 + k], av, acc[v]);
+          }
+        for (int off = ks >> 1; off; off >>= 1)
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (cb + u < C) acc[u] = fmaf(W3[(cb + u) * EL2 + k], av, acc[u]);
-        }
+          for (int v = 0; v < 4; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], off);
+        if (valid && slice == 0)
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (cb + u < C) zz[(cb + u) * TRP + tid] = acc[u];
+          for (int v = 0; v < 4; ++v)
+            if (cb + v < C) zz[(cb + v) * TRP + rr] = acc[v] + b3[cb + v];
       }
+      __syncthreads();
+      if (PH == 2 && kept) tile_store(a.z3raw, zz, C, r0, rows);
+    } else if (u.z) {
+      tile_load(zz, a.z3raw, C, r0, rows);
+      __syncthreads();
+    }
     if (PH == 2) {
-      for (int c = 0; c < C; ++c) {
-        const float v = act ? zz[c * TRP + tid] : 0.f;
-        stat_add(sacc, c, v);
-        stat_add(sacc, C + c, v * v);
-      }
+      chan_stats(sacc, C, TR, [&](int c, int rr, float& su, float& sv) {
+        const float x = rr < rows ? zz[c * TRP + rr] : 0.f;
+        su = x;
+        sv = x * x;
+      });
       continue;
     }
     if (PH == 3) {
       // ---- BN3 + positional encoding + dropout -> h[b,t,n,:] ----
-      if (act) {
-        float* hr = a.h + (size_t)r * C;
-        const size_t kbase = ((size_t)(b * N + n) * T + t) * C;     // reference dropout layout [B*N,T,C]
-        for (int c = 0; c < C; ++c) {
-          const float hn = fmaf(A3[c], zz[c * TRP + tid], C3[c]) + pe[t * C + c];
-          hr[c] = hn * keep_scale(a, kbase + c);
-        }
+      for (int o = tid; o < C * rows; o += kThreads) {
+        const int rr = o / C, c = o - rr * C;
+        const float hn = fmaf(A3[c], zz[c * TRP + rr], C3[c]) + pe[rowt[rr] * C + c];
+        // reference dropout layout [B*N,T,C]
+        a.h[(size_t)(r0 + rr) * C + c] = hn * keep_scale(a, (size_t)rowk[rr] * C + c);
       }
       continue;
     }
     if (BWD) {
-      // ---- dhn = dropout'(dh);  BN3 backward ----
-      const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
-      for (int c = 0; c < C; ++c) {
-        float dhn = 0.f, zh = 0.f;
-        if (act) {
-          dhn = a.dh[(size_t)r * C + c] * keep_scale(a, kbase + c);
-          zh = (zz[c * TRP + tid] - mu3[c]) * r3[c];
+      if (u.z2) {
+        // ---- dhn = dropout'(dh) ----
+        for (int o = tid; o < C * TR; o += kThreads) {
+          const int rr = o / C, c = o - rr * C;
+          z2[c * TRP + rr] = rr < rows ? a.dh[(size_t)(r0 + rr) * C + c] * keep_scale(a, (size_t)rowk[rr] * C + c) : 0.f;
         }
+        __syncthreads();
         if (PH == 4) {
-          stat_add(sacc, c, dhn);
-          stat_add(sacc, C + c, dhn * zh);
-        } else if (tid < TR) {
-          zz[c * TRP + tid] = act ? A3[c] * (dhn - q3[c] - zh * q3[C + c]) : 0.f;   // dz3
+          chan_stats(sacc, C, TR, [&](int c, int rr, float& su, float& sv) {
+            const float dhn = z2[c * TRP + rr];               // 0 past the end
+            su = dhn;
+            sv = dhn * (zz[c * TRP + rr] - mu3[c]) * r3[c];
+          });
+          continue;
         }
-      }
-      if (PH == 4) continue;
-      // ---- linear backward: da2 -> dn2 (ReLU) ----
-      if (tid < TR)
-        for (int k = 0; k < EL2; ++k) {
-          float v = 0.f;
-          if (act) {
-            const int e = k / L2;
-            if (fmaf(A2[e], c2[k * TRP + tid], C2[e]) > 0.f) {
-              for (int c = 0; c < C; ++c) v = fmaf(zz[c * TRP + tid], W3[c * EL2 + k], v);
-            }
-          }
-          d2[k * TRP + tid] = v;
-        }
-      if (PH == 5) {
-        for (int e = 0; e < E; ++e) {
-          float s = 0.f, sh = 0.f;
-          if (act)
-            for (int p = 0; p < L2; ++p) {
-              const float dn = d2[(e * L2 + p) * TRP + tid];
-              s += dn;
-              sh = fmaf(dn, (c2[(e * L2 + p) * TRP + tid] - mu2[e]) * r2[e], sh);
-            }
-          stat_add(sacc, e, s);
-          stat_add(sacc, E + e, sh);
+        // ---- BN3 backward -> dz3 (in zz) ----
+        for (int o = tid; o < C * TR; o += kThreads) {
+          const int rr = o & rmask, c = o >> lg;
+          const float zh = (zz[c * TRP + rr] - mu3[c]) * r3[c];
+          zz[c * TRP + rr] = rr < rows ? A3[c] * (z2[c * TRP + rr] - q3[c] - zh * q3[C + c]) : 0.f;
         }
         __syncthreads();
-        // dW3[c][k] += sum_r dz3[c][r] * a2[k][r];  db3[c] += sum_r dz3[c][r]
-        const int rows = min(TR, a.R - tile * TR);
-        pair_reduce(accW, C * EL2 + C, rows, [&](int pair, int rr) {
-          if (pair >= C * EL2) return zz[(pair - C * EL2) * TRP + rr];
-          const int c = pair / EL2, k = pair - c * EL2, e = k / L2;
-          const float av = fmaxf(fmaf(A2[e], c2[k * TRP + rr], C2[e]), 0.f);
-          return zz[c * TRP + rr] * av;
-        });
-        __syncthreads();
-        continue;
-      }
-      // ---- BN2 backward (in place) -> dc2 ----
-      if (tid < TR)
-        for (int k = 0; k < EL2; ++k) {
-          const int e = k / L2;
-          float v = 0.f;
-          if (act) {
-            const float ch2 = (c2[k * TRP + tid] - mu2[e]) * r2[e];
-            v = A2[e] * (d2[k * TRP + tid] - q2[e] - ch2 * q2[E + e]);
+        if (PH == 5) {
+          // dW3[c][k] += sum_r dz3[c][r] * a2[k][r]   (before a2 is overwritten): a thread owns (4 c, k) items
+          for (int it = tid; it < ncg * EL2; it += kThreads) {
+            const int cg = it / EL2, k = it - cg * EL2, cb = cg << 2;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int rr = 0; rr < rows; ++rr) {
+              const float av = a2[k * TRP + rr];
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                if (cb + v < C) acc[v] = fmaf(zz[(cb + v) * TRP + rr], av, acc[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              if (cb + v < C) accW[(cb + v) * EL2 + k] += acc[v];
           }
-          d2[k * TRP + tid] = v;
+          // db3[c] += sum_r dz3[c][r]
+          for (int c = tid; c < C; c += kThreads) {
+            float acc = 0.f;
+            for (int rr = 0; rr < rows; ++rr) acc += zz[c * TRP + rr];
+            accW[C * EL2 + c] += acc;
+          }
+          __syncthreads();
         }
-      // ---- conv2 backward wrt its input: da1 -> dn1 (ReLU) ----
-      if (tid < TR)
-        for (int ch = 0; ch < EH; ++ch)
-          for (int q = 0; q < L1; ++q) {
-            float v = 0.f;
-            if (act && fmaf(A1[ch], c1[(ch * L1 + q) * TRP + tid], C1[ch]) > 0.f) {
-              for (int e = 0; e < E; ++e)
-                for (int j = 0; j < K; ++j) {
-                  const int p = q - j + 1;
-                  if (p >= 0 && p < L2) v = fmaf(d2[(e * L2 + p) * TRP + tid], W2[(e * EH + ch) * K + j], v);
+        // ---- linear backward: da2 -> dn2 (ReLU mask = a2 > 0), in place over a2; 4 features per item ----
+        for (int o = tid; o < nkg * TR; o += kThreads) {
+          const int rr = o & rmask, k0 = (o >> lg) << 2;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          if (rr < rows)
+            for (int c = 0; c < C; ++c) {
+              const float dz = zz[c * TRP + rr];
+              const float* w = W3 + c * EL2 + k0;
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                if (k0 + v < EL2) acc[v] = fmaf(dz, w[v], acc[v]);
+            }
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (k0 + v < EL2) {
+              float* dst = d2 + (k0 + v) * TRP + rr;
+              *dst = (rr < rows && *dst > 0.f) ? acc[v] : 0.f;
+            }
+        }
+        __syncthreads();
+        if (PH == 5) {
+          if (kept) tile_store(a.dn2, d2, EL2, r0, rows);
+          chan_stats(sacc, E, L2 * TR, [&](int e, int i, float& su, float& sv) {
+            const int rr = i & rmask, k = e * L2 + (i >> lg);
+            const float dn = d2[k * TRP + rr];                // 0 past the end
+            su = dn;
+            sv = dn * (c2[k * TRP + rr] - mu2[e]) * r2[e];
+          });
+          continue;
+        }
+      } else if (PH == 6) {
+        tile_load(d2, a.dn2, EL2, r0, rows);
+        __syncthreads();
+      }
+      if (u.d2) {
+        // ---- BN2 backward (in place) -> dc2 ----
+        for (int o = tid; o < EL2 * TR; o += kThreads) {
+          const int rr = o & rmask, k = o >> lg, e = k / L2;
+          const float ch2 = (c2[k * TRP + rr] - mu2[e]) * r2[e];
+          d2[k * TRP + rr] = rr < rows ? A2[e] * (d2[k * TRP + rr] - q2[e] - ch2 * q2[E + e]) : 0.f;
+        }
+        __syncthreads();
+        // ---- conv2 backward wrt its input: da1 -> dn1 (ReLU mask = a1 > 0); 4 channels per item ----
+        for (int o = tid; o < nhg * L1 * TR; o += kThreads) {
+          const int rr = o & rmask, f = o >> lg, hg = f / L1, q = f - hg * L1, ch0 = hg << 2;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          if (rr < rows)
+            for (int e = 0; e < E; ++e)
+              for (int j = 0; j < K; ++j) {
+                const int p = q - j + 1;
+                if (p >= 0 && p < L2) {
+                  const float dv = d2[(e * L2 + p) * TRP + rr];
+                  const float* w = W2 + (e * EH + ch0) * K + j;
+#pragma unroll
+                  for (int v = 0; v < 4; ++v)
+                    if (ch0 + v < EH) acc[v] = fmaf(dv, w[v * K], acc[v]);
                 }
+              }
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (ch0 + v < EH) {
+              const int g = (ch0 + v) * L1 + q;
+              d1[g * TRP + rr] = (rr < rows && a1[g * TRP + rr] > 0.f) ? acc[v] : 0.f;
             }
-            d1[(ch * L1 + q) * TRP + tid] = v;
-          }
-      if (PH == 6) {
-        for (int ch = 0; ch < EH; ++ch) {
-          float s = 0.f, sh = 0.f;
-          if (act)
-            for (int p = 0; p < L1; ++p) {
-              const float dn = d1[(ch * L1 + p) * TRP + tid];
-              s += dn;
-              sh = fmaf(dn, (c1[(ch * L1 + p) * TRP + tid] - mu1[ch]) * r1[ch], sh);
-            }
-          stat_add(sacc, ch, s);
-          stat_add(sacc, EH + ch, sh);
         }
         __syncthreads();
-        // dW2[e][ch][j] += sum_r sum_p dc2[e][p][r] * a1[ch][p+j-1][r]
-        const int rows = min(TR, a.R - tile * TR);
-        pair_reduce(accW, E * EH * K, rows, [&](int pair, int rr) {
-          const int j = pair % K, ech = pair / K, ch = ech % EH, e = ech / EH;
-          float acc = 0.f;
-          for (int p = 0; p < L2; ++p) {
-            const int q = p + j - 1;
-            if (q >= 0 && q < L1) {
-              const float av = fmaxf(fmaf(A1[ch], c1[(ch * L1 + q) * TRP + rr], C1[ch]), 0.f);
-              acc = fmaf(d2[(e * L2 + p) * TRP + rr], av, acc);
-            }
-          }
-          return acc;
-        });
+      } else {
+        tile_load(d1, a.dn1, NL1, r0, rows);                  // B4 with kept activations
         __syncthreads();
+      }
+      if (PH == 6) {
+        if (kept) tile_store(a.dn1, d1, NL1, r0, rows);
+        chan_stats(sacc, EH, L1 * TR, [&](int ch, int i, float& su, float& sv) {
+          const int rr = i & rmask, f = ch * L1 + (i >> lg);
+          const float dn = d1[f * TRP + rr];                  // 0 past the end
+          su = dn;
+          sv = dn * (c1[f * TRP + rr] - mu1[ch]) * r1[ch];
+        });
+        // dW2[e][ch][j] += sum_r sum_p dc2[e][p][r] * a1[ch][p+j-1][r]
+        pair_reduce(accW, E * EH * K, rows, [&](int pair) {
+          const int j = pair % K, ech = pair / K, ch = ech % EH, e = ech / EH;
+          const int p0 = imax(0, 1 - j), p1 = min(L2, L1 + 1 - j);          // 0 <= p + j - 1 < L1
+          const float* dv = d2 + (e * L2) * TRP;
+          const float* av = a1 + (ch * L1 + j - 1) * TRP;
+          return [=](int rr) {
+            float acc = 0.f;
+            for (int p = p0; p < p1; ++p) acc = fmaf(dv[p * TRP + rr], av[p * TRP + rr], acc);
+            return acc;
+          };
+        });
         continue;
       }
       // ---- PH == 7: BN1 backward -> dc1; dW1[ch][j] += sum_r sum_p dc1[ch][p][r] * xpad[p+j-pad1][r]
-      if (tid < TR)
-        for (int ch = 0; ch < EH; ++ch)
-          for (int p = 0; p < L1; ++p) {
-            float v = 0.f;
-            if (act) {
-              const float ch1 = (c1[(ch * L1 + p) * TRP + tid] - mu1[ch]) * r1[ch];
-              v = A1[ch] * (d1[(ch * L1 + p) * TRP + tid] - q1[ch] - ch1 * q1[EH + ch]);
-            }
-            d1[(ch * L1 + p) * TRP + tid] = v;
-          }
+      for (int o = tid; o < NL1 * TR; o += kThreads) {
+        const int rr = o & rmask, f = o >> lg, ch = f / L1;
+        const float ch1 = (c1[f * TRP + rr] - mu1[ch]) * r1[ch];
+        d1[f * TRP + rr] = rr < rows ? A1[ch] * (d1[f * TRP + rr] - q1[ch] - ch1 * q1[EH + ch]) : 0.f;
+      }
       __syncthreads();
-      const int rows = min(TR, a.R - tile * TR);
-      pair_reduce(accW, EH * K, rows, [&](int pair, int rr) {
+      pair_reduce(accW, EH * K, rows, [&](int pair) {
         const int j = pair % K, ch = pair / K;
-        float acc = 0.f;
-        for (int p = 0; p < L1; ++p) {
-          const int q = p + j - a.pad1;
-          if (q >= 0 && q < P) acc = fmaf(d1[(ch * L1 + p) * TRP + rr], xs[q * TRP + rr], acc);
-        }
-        return acc;
+        const int p0 = imax(0, a.pad1 - j), p1 = min(L1, P + a.pad1 - j);   // 0 <= p + j - pad1 < P
+        const float* dv = d1 + (ch * L1) * TRP;
+        const float* xv = xs + (j - a.pad1) * TRP;
+        return [=](int rr) {
+          float acc = 0.f;
+          for (int p = p0; p < p1; ++p) acc = fmaf(dv[p * TRP + rr], xv[p * TRP + rr], acc);
+          return acc;
+        };
       });
-      __syncthreads();
     }
   }
   __syncthreads();
@@ -469,7 +615,10 @@ int num_sms() {
   return sms[dev];
 }
 
-void launch_phase(int ph, const EncArgs& a, size_t smem, cudaStream_t s) {
+void launch_phase(int ph, const EncArgs& a0, cudaStream_t s) {
+  EncArgs a = a0;
+  a.TR = tile_rows_for(a0, ph);                   // plan_encoder checked that every phase fits
+  const size_t smem = (size_t)make_lay(a, ph).total * 4;
   const int ntiles = (a.R + a.TR - 1) / a.TR;
   // persistent CTAs: as many as fit (shared memory bound), never more than tiles
   int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -494,14 +643,12 @@ int plan_encoder(EncArgs& a, size_t* smem_fwd, size_t* smem_bwd, char* err, size
   }
   a.EL2 = a.E * a.L2;
   a.R = a.B * a.T * a.N;
-  for (int tr = 256; tr >= 8; tr >>= 1) {
-    a.TR = tr;
-    const size_t sb = (size_t)make_lay(a, true).total * 4;
-    if (sb <= kSmemCap) {
-      *smem_fwd = (size_t)make_lay(a, false).total * 4;
-      *smem_bwd = sb;
-      return 0;
-    }
+  bool fits = true;
+  for (int ph = 0; ph < 8 && fits; ++ph) fits = tile_rows_for(a, ph) > 0;
+  if (fits) {
+    a.TR = tile_rows_for(a, 7);
+    *smem_fwd = *smem_bwd = 0;                    // chosen per phase at launch
+    return 0;
   }
   snprintf(err, errlen, "encoder tile does not fit shared memory (P=%d K=%d EH=%d E=%d C=%d)", a.P, a.K, a.EH, a.E, a.C);
   return -2;
@@ -511,15 +658,15 @@ int launch_encoder_forward(const EncArgs& a, size_t smem, cudaStream_t s) {
   if (a.c2raw && encoder_fast_available(a)) return launch_encoder_fast(a, false, s);
   set_attrs();
   if (a.training)
-    for (int ph = 0; ph < 3; ++ph) launch_phase(ph, a, smem, s);
-  launch_phase(3, a, smem, s);
+    for (int ph = 0; ph < 3; ++ph) launch_phase(ph, a, s);
+  launch_phase(3, a, s);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
 int launch_encoder_backward(const EncArgs& a, size_t smem, cudaStream_t s) {
   if (a.c2raw && encoder_fast_available(a)) return launch_encoder_fast(a, true, s);
   set_attrs();
-  for (int ph = 4; ph < 8; ++ph) launch_phase(ph, a, smem, s);
+  for (int ph = 4; ph < 8; ++ph) launch_phase(ph, a, s);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -622,6 +622,8 @@ using D_FD003 = EncDims<1, 2, 8, 6, 48>;   // hparams.py:109-111
 }  // namespace
 
 bool encoder_fast_available(const EncArgs& a) {
+  static const bool off = getenv("STG_ENC_GENERIC") != nullptr;      // tests: force the any-dimension kernels
+  if (off) return false;
   return matches<D_FD004>(a) || matches<D_S2>(a) || matches<D_FD002>(a) || matches<D_FD003>(a);
 }
 

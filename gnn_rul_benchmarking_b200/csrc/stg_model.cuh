@@ -25,7 +25,8 @@ struct EncArgs {
   int training;
   float momentum, eps;
   double* st;                 // stats scratch, see enc_stat_off()
-  // fast path only: raw activations / masked gradients kept between phases, [tile][feature][256]
+  // raw activations / masked gradients kept between phases in training: [tile][feature][256] (fast path),
+  // [row][feature] (any-dimension kernels)
   float *c2raw, *z3raw, *dn2, *dn1;
   float* h;                   // [R, C] output of the forward
   const float* dh;            // [R, C] gradient wrt h

@@ -1,6 +1,8 @@
 """GPU parity of the whole-model engine (encoder + blocks + head + MSE + Adam in libstgconv_b200.so)
 against the CPU oracle: every reference FC_STGNN hyper-parameter set, the fused update rule over
 several optimisation steps, eval/train switching, running statistics, dropout handling."""
+import os
+
 import pytest
 import torch
 
@@ -215,3 +217,17 @@ def test_cuda_graph_step_matches_eager_and_preserves_state():
     algs[1].load_state_dict(sd)
     lb = algs[1].update(X, y, 0)["loss"]
     assert abs(la - lb) > 1e-7
+
+
+def test_any_dimension_encoder_on_every_config():
+    """STG_ENC_GENERIC=1 routes the register-path hyper-parameter sets through the any-dimension encoder
+    kernels too (read once per process, hence the subprocess): the oracle comparison must hold on all of them."""
+    import subprocess
+    import sys
+    if os.environ.get("STG_ENC_GENERIC"):
+        pytest.skip("already inside the forced run")
+    env = dict(os.environ, STG_ENC_GENERIC="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.abspath(__file__), "-k",
+                        "test_model_forward_backward_vs_oracle or test_fused_update or test_cuda_graph"], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
