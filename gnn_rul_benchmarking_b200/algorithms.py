@@ -115,9 +115,14 @@ class FC_STGNN(Algorithm):
             for _ in range(2):
                 self._eager_step(self._gX, self._gy)
         torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
+        self._hloss = torch.zeros(1, dtype=torch.float32).pin_memory()    # update()'s loss lands here
+        graph = torch.cuda.CUDAGraph()                  # step(): loss stays on the device
         with torch.cuda.graph(graph):
             self._gloss = self._eager_step(self._gX, self._gy)
+        graph_u = torch.cuda.CUDAGraph()                # update(): the D2H read of the loss is a node of the graph
+        with torch.cuda.graph(graph_u):
+            self._gloss_u = self._eager_step(self._gX, self._gy)
+            self._hloss.copy_(self._gloss_u.reshape(1), non_blocking=True)
         with torch.no_grad():
             for t, s0 in zip((fl["param"], st["exp_avg"], st["exp_avg_sq"], st["step"]), snap):
                 t.copy_(s0)
@@ -125,25 +130,31 @@ class FC_STGNN(Algorithm):
                 b.copy_(s0)
             eng.graph_seed[1].zero_()
         self.train(was_training)
-        self._graph, self._graph_bs = graph, batch_size
+        self._graph, self._graph_u, self._graph_bs = graph, graph_u, batch_size
 
     def disable_cuda_graph(self):
-        self._graph = None
+        self._graph = self._graph_u = None
         self.model.engine.graph_seed = None
+
+    def _graph_ready(self, X):
+        return getattr(self, "_graph", None) is not None and X.shape[0] == self._graph_bs and self.training
 
     def step(self, X, y):
         """One optimisation step (forward -> MSE -> backward -> [all-reduce] -> Adam) with everything
-        left on the device; returns the loss as a 0-dim device tensor."""
-        g = getattr(self, "_graph", None)
-        if g is not None and X.shape[0] == self._graph_bs and self.training:
+        left on the device; returns the loss as a 0-dim device tensor.  X, y may be device tensors or
+        (pinned) host tensors: with the graph enabled they are copied straight into its input buffers."""
+        if self._graph_ready(X):
             self._gX.copy_(X, non_blocking=True)
             self._gy.copy_(y.reshape(self._gy.shape), non_blocking=True)
-            g.replay()
+            self._graph.replay()
             return self._gloss
         return self._eager_step(X, y)
 
     def _eager_step(self, X, y):
         eng = self.model.engine
+        dev = next(self.model.parameters()).device
+        if X.device != dev:
+            X, y = X.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
         loss = eng.loss_backward(X, y, zero_grad=True)
         if self._dp_world > 1 and not getattr(self, "_dp_p2p", False):
             import torch.distributed as dist
@@ -152,6 +163,12 @@ class FC_STGNN(Algorithm):
         return loss
 
     def update(self, X, y, epoch=None):
+        if self._graph_ready(X):
+            self._gX.copy_(X, non_blocking=True)
+            self._gy.copy_(y.reshape(self._gy.shape), non_blocking=True)
+            self._graph_u.replay()
+            torch.cuda.current_stream(self._gX.device).synchronize()
+            return {"loss": float(self._hloss[0])}
         return {"loss": self.step(X, y).item()}
 
 
