@@ -499,6 +499,274 @@ __global__ void __launch_bounds__(256) k_zero(float4* p, size_t n4, const TickAr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Wide heads (J > 32, e.g. FD003: F = 24 864, J = 48).  There fc1 and its backward are real GEMMs and the
+// one-thread-per-column kernels above run out of registers / re-read W1 once per sample; these versions tile
+// them through shared memory with register blocking.
+constexpr int kWT = 256;            // threads
+constexpr int kWBM = 128;           // samples per CTA tile (fc1)
+constexpr int kWKC = 32;            // contraction chunk (fc1)
+constexpr int kWFP = kWBM + 4;      // pitch of the transposed feature tile (16-byte aligned rows)
+
+// z1[b][j] += sum_{k in slice} feat[b][k] W1[j][k] (+ b1[j] from slice 0).  grid (ceil(B/128), KSPLIT).
+// Thread (tx = tid%16, ty = tid/16): JQ = JP/16 outputs j = tx*JQ.. for the 8 samples ty*8.. of the tile.
+template <int JP, bool FUSED>
+__global__ void __launch_bounds__(kWT) k_head_fc1_wide(const HeadArgs a, int kper) {
+  constexpr int JQ = JP / 16;
+  __shared__ __align__(16) float fT[kWKC][kWFP];     // feat tile, [k][sample]
+  __shared__ float Ws[JP][kWKC + 1];                 // W1 tile, [j][k]
+  __shared__ float bc[2][4][64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, J = a.J, F = a.F;
+  const int b0 = blockIdx.x * kWBM;
+  const int k_lo = blockIdx.y * kper, k_hi = min(F, k_lo + kper);
+  if (FUSED) head_bn1(a, bc, blockIdx.x == 0 && blockIdx.y == 0);
+  float acc[8][JQ];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int u = 0; u < JQ; ++u) acc[i][u] = 0.f;
+  const int pk = tid & 31, pb = tid >> 5;            // producer: column pk of the chunk, samples pb + 8*i
+  for (int kc = k_lo; kc < k_hi; kc += kWKC) {
+    __syncthreads();                                 // previous chunk consumed (and bc ready)
+    {
+      const int k = kc + pk;
+      const bool kin = k < k_hi;
+      const float* yp = nullptr;
+      size_t jst = 0, bst = 0;
+      float a1 = 0.f, c1 = 0.f, invw = 1.f;
+      int w = 0;
+      if (FUSED && kin) {
+        const int z = (a.nblk > 1 && k >= a.blk[1].foff) ? 1 : 0;
+        const HeadBlk& kb = a.blk[z];
+        const int e = k - kb.foff, h = e % kb.H, ln = e / kb.H, n = ln % kb.N, l = ln / kb.N;
+        a1 = bc[z][0][h]; c1 = bc[z][1][h];
+        w = kb.w; invw = 1.f / (float)w;
+        jst = (size_t)kb.N * kb.H;
+        bst = (size_t)kb.L * kb.M * kb.H;
+        yp = kb.yp + ((size_t)l * kb.M + n) * kb.H + h;
+      }
+#pragma unroll 4
+      for (int i = 0; i < kWBM / 8; ++i) {
+        const int bl = pb + 8 * i, b = b0 + bl;
+        float v = 0.f;
+        if (kin && b < a.B) {
+          if (FUSED) {
+            const float* y = yp + (size_t)b * bst;
+            for (int j = 0; j < w; ++j) v += lrelu(fmaf(a1, y[j * jst], c1));
+            v *= invw;
+            a.feat_out[(size_t)b * F + k] = v;
+          } else {
+            v = a.feat[(size_t)b * F + k];
+          }
+        }
+        fT[pk][bl] = v;
+      }
+      for (int j = pb; j < JP; j += 8) Ws[j][pk] = (kin && j < J) ? a.W1[(size_t)j * F + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < kWKC; ++kk) {
+      const float4 f0 = *reinterpret_cast<const float4*>(&fT[kk][ty * 8]);
+      const float4 f1 = *reinterpret_cast<const float4*>(&fT[kk][ty * 8 + 4]);
+      const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+      for (int u = 0; u < JQ; ++u) {
+        const float wv = Ws[tx * JQ + u][kk];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][u] = fmaf(f[i], wv, acc[i][u]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int b = b0 + ty * 8 + i;
+#pragma unroll
+    for (int u = 0; u < JQ; ++u) {
+      const int j = tx * JQ + u;
+      if (b < a.B && j < J) atomicAdd(&a.z1[(size_t)b * J + j], acc[i][u] + (blockIdx.y == 0 ? a.b1[j] : 0.f));
+    }
+  }
+}
+
+// One CTA per 128 feature columns, all samples (d1 given in a.d1 by k_head_tail):
+//   dfeat[b][k] = sum_j d1[b][j] W1[j][k]      thread (kx = tid%32 -> 4 columns, by = tid/32 -> 8 samples of a 64-chunk)
+//   dW1[j][k]  += sum_b d1[b][j] feat[b][k]    thread (kx -> 4 columns, jy = tid/32 -> JP/8 rows j), no atomics
+// FUSED: BatchNorm-1 backward sums of the graph-conv blocks from dfeat and the saved Y' (as k_head_bwd1).
+constexpr int kWBC = 64;            // samples per chunk (bwd1)
+template <int JP, bool FUSED>
+__global__ void __launch_bounds__(kWT, 2) k_head_bwd1_wide(const HeadArgs a) {
+  constexpr int JR = JP / 8;
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                         // [JP][128]
+  float* fs = Ws + JP * 128;              // [64][128]
+  float* ds = fs + kWBC * 128;            // [64][JP]
+  __shared__ float bc[2][4][64];
+  __shared__ float sred[2][2][64];
+  const int tid = threadIdx.x, kx = tid & 31, wy = tid >> 5, J = a.J, F = a.F;
+  const int k0 = blockIdx.x * 128, kq = k0 + kx * 4;
+  if (FUSED) {
+    head_bn1(a, bc, false);
+    for (int i = tid; i < 2 * 2 * 64; i += kWT) (&sred[0][0][0])[i] = 0.f;
+  }
+  for (int i = tid; i < JP * 128; i += kWT) {
+    const int j = i >> 7, c = i & 127;
+    Ws[i] = (j < J && k0 + c < F) ? a.W1[(size_t)j * F + k0 + c] : 0.f;
+  }
+  __syncthreads();
+  // per-column constants of the fused statistics (shared: the register file is needed for the two tiles)
+  __shared__ unsigned cyo[128];
+  __shared__ int cjst[128], cbst[128], cwz[128];          // cwz = w | z << 8 | h << 16
+  __shared__ float ccf[4][128];                           // a1, c1, mu, r1
+  if (FUSED && tid < 128) {
+    const int k = k0 + tid;
+    cyo[tid] = 0; cjst[tid] = cbst[tid] = 0; cwz[tid] = 0;
+    ccf[0][tid] = ccf[1][tid] = ccf[2][tid] = ccf[3][tid] = 0.f;
+    if (k < F) {
+      const int z = (a.nblk > 1 && k >= a.blk[1].foff) ? 1 : 0;
+      const HeadBlk& kb = a.blk[z];
+      const int e = k - kb.foff, h = e % kb.H, ln = e / kb.H, n = ln % kb.N, l = ln / kb.N;
+      cyo[tid] = (unsigned)((l * kb.M + n) * kb.H + h);
+      cjst[tid] = kb.N * kb.H;
+      cbst[tid] = kb.L * kb.M * kb.H;
+      cwz[tid] = kb.w | (z << 8) | (h << 16);
+      ccf[0][tid] = bc[z][0][h]; ccf[1][tid] = bc[z][1][h]; ccf[2][tid] = bc[z][2][h]; ccf[3][tid] = bc[z][3][h];
+    }
+  }
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float gw[JR][4];
+#pragma unroll
+  for (int u = 0; u < JR; ++u)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gw[u][q] = 0.f;
+
+  for (int bc0 = 0; bc0 < a.B; bc0 += kWBC) {
+    const int nb = min(kWBC, a.B - bc0);
+    __syncthreads();
+    for (int i = tid; i < kWBC * 128; i += kWT) {
+      const int bl = i >> 7, c = i & 127;
+      fs[i] = (bl < nb && k0 + c < F) ? a.feat[(size_t)(bc0 + bl) * F + k0 + c] : 0.f;
+    }
+    for (int i = tid; i < kWBC * JP; i += kWT) {
+      const int bl = i / JP, j = i - bl * JP;
+      ds[i] = (bl < nb && j < J) ? a.d1[(size_t)(bc0 + bl) * J + j] : 0.f;
+    }
+    __syncthreads();
+    // ---- dfeat for samples wy*8 .. wy*8+7 of the chunk, columns kq..kq+3
+    {
+      float df[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) df[i][q] = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < JP; ++j) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&Ws[j * 128 + kx * 4]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dj = ds[(wy * 8 + i) * JP + j];
+          df[i][0] = fmaf(dj, w4.x, df[i][0]);
+          df[i][1] = fmaf(dj, w4.y, df[i][1]);
+          df[i][2] = fmaf(dj, w4.z, df[i][2]);
+          df[i][3] = fmaf(dj, w4.w, df[i][3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int bl = wy * 8 + i, b = bc0 + bl;
+        if (bl < nb) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (kq + q < F) {
+              a.dfeat[(size_t)b * F + kq + q] = df[i][q];
+              if (FUSED) {
+                const int c = kx * 4 + q, wz = cwz[c], w = wz & 255;
+                const float* y = ((wz >> 8) & 1 ? a.blk[1].yp : a.blk[0].yp) + (size_t)b * cbst[c] + cyo[c];
+                const float invw = 1.f / (float)w, ca = ccf[0][c], cc = ccf[1][c], cm = ccf[2][c], cr = ccf[3][c];
+                for (int jj = 0; jj < w; ++jj) {
+                  const float yv = y[jj * cjst[c]];
+                  const float dyn = df[i][q] * invw * (fmaf(ca, yv, cc) > 0.f ? 1.f : kLeaky);
+                  s1[q] += dyn;
+                  s2[q] = fmaf(dyn, (yv - cm) * cr, s2[q]);
+                }
+              }
+            }
+        }
+      }
+    }
+    // ---- dW1 rows wy*JR .. wy*JR+JR-1, columns kq..kq+3, over this chunk's samples
+#pragma unroll 4
+    for (int bl = 0; bl < kWBC; ++bl) {
+      const float4 f4 = *reinterpret_cast<const float4*>(&fs[bl * 128 + kx * 4]);
+#pragma unroll
+      for (int u = 0; u < JR; ++u) {
+        const float dj = ds[bl * JP + wy * JR + u];
+        gw[u][0] = fmaf(dj, f4.x, gw[u][0]);
+        gw[u][1] = fmaf(dj, f4.y, gw[u][1]);
+        gw[u][2] = fmaf(dj, f4.z, gw[u][2]);
+        gw[u][3] = fmaf(dj, f4.w, gw[u][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < JR; ++u) {
+    const int j = wy * JR + u;
+    if (j < J)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (kq + q < F) a.dW1[(size_t)j * F + kq + q] += gw[u][q];      // this CTA is the column's only writer
+  }
+  if (FUSED) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (kq + q < F) {
+        const int wz = cwz[kx * 4 + q];
+        atomicAdd(&sred[(wz >> 8) & 1][0][wz >> 16], s1[q]);
+        atomicAdd(&sred[(wz >> 8) & 1][1][wz >> 16], s2[q]);
+      }
+    __syncthreads();
+    for (int i = tid; i < a.nblk * 64; i += kWT) {
+      const int z = i >> 6, h = i & 63;
+      const HeadBlk& kb = a.blk[z];
+      if (h < kb.H) {
+        atomicAdd(&kb.stats[2 * kb.H + h], (double)sred[z][0][h]);
+        atomicAdd(&kb.stats[3 * kb.H + h], (double)sred[z][1][h]);
+      }
+    }
+  }
+}
+
+template <int JP>
+void fc1_wide_launch(const HeadArgs& a, cudaStream_t s) {
+  const int gx = (a.B + kWBM - 1) / kWBM;
+  int ksplit = (2 * 148 + gx - 1) / gx;
+  if (const char* e = getenv("STG_FC1_KSPLIT")) { const int v = atoi(e); if (v >= 1) ksplit = v; }
+  const int maxsplit = (a.F + 4 * kWKC - 1) / (4 * kWKC);
+  if (ksplit > maxsplit) ksplit = maxsplit;
+  if (ksplit < 1) ksplit = 1;
+  const int kper = (((a.F + ksplit - 1) / ksplit) + kWKC - 1) / kWKC * kWKC;
+  ksplit = (a.F + kper - 1) / kper;
+  if (a.fused_blocks) k_head_fc1_wide<JP, true><<<dim3(gx, ksplit), kWT, 0, s>>>(a, kper);
+  else k_head_fc1_wide<JP, false><<<dim3(gx, ksplit), kWT, 0, s>>>(a, kper);
+}
+template <int JP>
+void bwd1_wide_launch(const HeadArgs& a, cudaStream_t s) {
+  const size_t smem = (size_t)(JP * 128 + kWBC * 128 + kWBC * JP) * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_head_bwd1_wide<JP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_head_bwd1_wide<JP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  const int gx = (a.F + 127) / 128;
+  if (a.fused_blocks) k_head_bwd1_wide<JP, true><<<gx, kWT, smem, s>>>(a);
+  else k_head_bwd1_wide<JP, false><<<gx, kWT, smem, s>>>(a);
+}
+inline bool head_wide(const HeadArgs& a) {
+  static const bool off = getenv("STG_HEAD_NARROW") != nullptr;
+  return !off && a.J > 32 && a.F >= 2048;
+}
+
 template <int JP, int SPB>
 void fc1_launch(const HeadArgs& a, cudaStream_t s) {
   const int gx = (a.B + SPB - 1) / SPB;
@@ -559,7 +827,8 @@ int launch_head_forward(const HeadArgs& a, cudaStream_t s) {
   if (a.J > 64 || a.H > 64) return -2;
   {
     ProfScope ps(kProfHeadFc1, s);
-    if (a.J <= 16) fc1_launch<16, 2>(a, s);
+    if (head_wide(a)) { if (a.J <= 48) fc1_wide_launch<48>(a, s); else fc1_wide_launch<64>(a, s); }
+    else if (a.J <= 16) fc1_launch<16, 2>(a, s);
     else if (a.J <= 32) fc1_launch<32, 2>(a, s);
     else if (a.J <= 48) fc1_launch<48, 1>(a, s);
     else fc1_launch<64, 1>(a, s);
@@ -577,13 +846,15 @@ int launch_head_backward(const HeadArgs& a, cudaStream_t s) {
   if (a.J > 64 || a.H > 64) return -2;
   tail_attrs();
   const int TB = tail_tb(a.J);
-  if (!a.fused_blocks) {                 // op path: separate tail kernel writes d1
+  const bool wide = head_wide(a);
+  if (!a.fused_blocks || wide) {         // op path / wide heads: separate tail kernel writes d1
     ProfScope ps(kProfHeadTail, s);
     if (a.y) k_head_tail<2><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
     else k_head_tail<1><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
   }
   ProfScope ps(kProfHeadBwd1, s);
-  if (a.J <= 16) bwd1_launch<16>(a, s);
+  if (wide) { if (a.J <= 48) bwd1_wide_launch<48>(a, s); else bwd1_wide_launch<64>(a, s); }
+  else if (a.J <= 16) bwd1_launch<16>(a, s);
   else if (a.J <= 32) bwd1_launch<32>(a, s);
   else if (a.J <= 48) bwd1_launch<48>(a, s);
   else bwd1_launch<64>(a, s);
