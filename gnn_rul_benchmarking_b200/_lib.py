@@ -117,6 +117,14 @@ MODEL_SIGNATURES["stg_tcn_backward"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_in
                                                   C.POINTER(StgTcnParams), C.POINTER(StgTcnParams), C.c_float,
                                                   C.c_void_p, C.c_void_p, C.c_void_p])
 MODEL_SIGNATURES["stg_patch_stats"] = (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p])
+MODEL_SIGNATURES["stg_patch_stats11"] = (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p])
+MODEL_SIGNATURES["stg_gat_forward"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                 C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                                 C.c_void_p, C.c_void_p])
+MODEL_SIGNATURES["stg_gat_backward"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                  C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p])
 SIGNATURES.update(MODEL_SIGNATURES)
 
 _lib = None

@@ -229,4 +229,17 @@ class STMSGCN(ASTGCNN):
         self.hparams = hparams
 
 
-_ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN, "ST_GCN": ST_GCN, "STGNN": STGNN, "STMSGCN": STMSGCN}
+class GAT_LSTM(ASTGCNN):
+    """reference algorithms.py class GAT_LSTM: same update rule around GAT_LSTM_model (gat_lstm.py)."""
+
+    def __init__(self, configs, hparams, device):
+        Algorithm.__init__(self, configs)
+        from .gat_lstm import GAT_LSTM_model
+        self.model = GAT_LSTM_model(**configs)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
+                                          weight_decay=hparams["weight_decay"])
+        self.hparams = hparams
+
+
+_ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN, "ST_GCN": ST_GCN, "STGNN": STGNN, "STMSGCN": STMSGCN,
+               "GAT_LSTM": GAT_LSTM}

@@ -169,3 +169,62 @@ def segment_and_compute_features(data: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().stg_patch_stats(x.data_ptr(), R, P, out.data_ptr(), _stream()), "stg_patch_stats")
     return out
+
+
+def extract_features(data: torch.Tensor) -> torch.Tensor:
+    """models/GAT_LSTM/Model.py:6-70: data [rows, patch_size] -> [rows, 11] statistics (forward only)."""
+    if not data.is_cuda:
+        raise RuntimeError("patch statistics run on the device (no CPU fallback)")
+    x = data.detach().contiguous().float()
+    R, P = x.shape
+    out = torch.empty(R, 11, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().stg_patch_stats11(x.data_ptr(), R, P, out.data_ptr(), _stream()), "stg_patch_stats11")
+    return out
+
+
+class _GatAttention(torch.autograd.Function):
+    """stg_gat_forward / stg_gat_backward: everything of GraphAttentionLayer.forward after its nn.Linear."""
+
+    @staticmethod
+    def forward(ctx, Wh, att_w, att_b, adj, keep, pdrop, alpha, out_slope):
+        if not Wh.is_cuda:
+            raise RuntimeError("graph attention runs on the device (no CPU fallback)")
+        Wh = Wh.contiguous().float()
+        G, N, F = Wh.shape
+        aw, ab = att_w.contiguous().float().view(-1), att_b.contiguous().float().view(-1)
+        adj = adj.detach().contiguous().float()
+        per_graph = 1 if adj.dim() == 3 else 0
+        if adj.shape[-2:] != (N, N) or (per_graph and adj.shape[0] != G) or aw.numel() != 2 * F:
+            raise ValueError("graph attention: inconsistent shapes")
+        keep = None if keep is None else keep.detach().contiguous().float()
+        out = torch.empty_like(Wh)
+        with torch.cuda.device(Wh.device):
+            _lib.check(_lib.load().stg_gat_forward(Wh.data_ptr(), aw.data_ptr(), ab.data_ptr(), adj.data_ptr(), per_graph,
+                                                   0 if keep is None else keep.data_ptr(), float(pdrop), float(alpha),
+                                                   float(out_slope), G, N, F, out.data_ptr(), _stream()),
+                       "stg_gat_forward")
+        ctx.save_for_backward(Wh, aw, ab, adj, keep if keep is not None else Wh.new_empty(0), out)
+        ctx.cfg = (per_graph, keep is not None, float(pdrop), float(alpha), float(out_slope), att_w.shape, att_b.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Wh, aw, ab, adj, keep, out = ctx.saved_tensors
+        per_graph, has_keep, pdrop, alpha, out_slope, wshape, bshape = ctx.cfg
+        G, N, F = Wh.shape
+        dout = dout.contiguous().float()
+        dWh = torch.empty_like(Wh)
+        daw, dab = torch.zeros_like(aw), torch.zeros_like(ab)
+        with torch.cuda.device(Wh.device):
+            _lib.check(_lib.load().stg_gat_backward(Wh.data_ptr(), aw.data_ptr(), ab.data_ptr(), adj.data_ptr(), per_graph,
+                                                    keep.data_ptr() if has_keep else 0, pdrop, alpha, out_slope, G, N, F,
+                                                    out.data_ptr(), dout.data_ptr(), dWh.data_ptr(), daw.data_ptr(),
+                                                    dab.data_ptr(), _stream()), "stg_gat_backward")
+        return dWh, daw.view(wshape), dab.view(bshape), None, None, None, None, None
+
+
+def gat_attention(Wh, att_w, att_b, adj, keep=None, pdrop=0.0, alpha=0.1, out_slope=0.01):
+    """leaky_relu((dropout(softmax_j(leaky_relu_alpha(a.[Wh_i || Wh_j] + b))) * adj) Wh): Wh [G,N,F], att_w [1,2F]
+    (nn.Linear(2F,1).weight), att_b [1], adj [N,N] or [G,N,N], keep = 0/1 mask [G,N,N] of the attention dropout."""
+    return _GatAttention.apply(Wh, att_w, att_b, adj, keep, pdrop, alpha, out_slope)

@@ -261,6 +261,25 @@ int stg_tcn_backward(const float* x_dev, const float* dout_dev, int B, int C, in
  * (models/ST_GCN/Model.py:7-52).  x [R, P] -> out [R, 10] = max, min, ptp, var, std (unbiased), mean, rms,
  * mean|x|, skewness, excess kurtosis.  Forward only (no parameter upstream). */
 int stg_patch_stats(const float* x_dev, int64_t R, int P, float* out_dev, void* stream);
+/* extract_features (models/GAT_LSTM/Model.py:6-70): x [R, P] -> out [R, 11] = mean, std (unbiased),
+ * (mean sqrt|x|)^2, rms, (max-min)/2, skewness, kurtosis (the reference's sample-size coefficients), crest,
+ * clearance, shape and impulse factors.  Forward only. */
+int stg_patch_stats11(const float* x_dev, int64_t R, int P, float* out_dev, void* stream);
+
+/* Dense graph attention (primitive M5): GraphAttentionLayer.forward after its nn.Linear
+ * (models/GAT_LSTM/Model.py:87-109).  Wh [G,N,F]; att_w [2F], att_b [1] = GraphAttentionLayer.attention;
+ * adj [N,N] shared by all graphs (adj_per_graph = 0) or [G,N,N]; keep = 0/1 dropout mask [G,N,N] of the
+ * attention matrix (NULL: no dropout), scaled by 1/(1-pdrop) inside; alpha = slope of the score leaky_relu,
+ * out_slope (> 0) = slope of the output leaky_relu.
+ *   out = leaky_relu_{out_slope}((dropout(softmax_j(leaky_relu_alpha(a1.Wh_i + a2.Wh_j + b))) * adj) Wh)
+ * backward: dWh written, datt_w [2F] / datt_b [1] ACCUMULATED into. */
+int stg_gat_forward(const float* Wh_dev, const float* att_w_dev, const float* att_b_dev, const float* adj_dev,
+                    int adj_per_graph, const float* keep_dev, float pdrop, float alpha, float out_slope,
+                    int G, int N, int F, float* out_dev, void* stream);
+int stg_gat_backward(const float* Wh_dev, const float* att_w_dev, const float* att_b_dev, const float* adj_dev,
+                     int adj_per_graph, const float* keep_dev, float pdrop, float alpha, float out_slope,
+                     int G, int N, int F, const float* out_dev, const float* dout_dev, float* dWh_dev,
+                     float* datt_w_dev, float* datt_b_dev, void* stream);
 
 /* Evaluation metrics (utils.py:136-169, called every epoch from trainer.py:119-121): ACCUMULATES into
  * out4_dev (4 doubles, caller zeroes): [0] sum of Score_v1 terms, [1] sum of Score_v2 terms,

@@ -282,6 +282,64 @@ def aux_golden():
         for k, p in mdl.named_parameters():
             if p.grad is not None:
                 out[f"{tag}/grad/{k}"] = _np(p.grad)
+    # GAT_LSTM (BASELINE configs[3], PHM2012 hparams): 11 patch statistics, one attention layer, the whole model.
+    # The reference draws its attention dropout with F.dropout; the module-level name F of the imported reference
+    # module is re-bound (in this process only) to a namespace whose dropout applies the recorded masks.
+    import types
+    import models.GAT_LSTM.Model as gat_ref                         # noqa: E402
+    Fn = torch.nn.functional
+    masks = []
+
+    def pinned_dropout(att, p, training=True):
+        if not training:
+            return att
+        keep = (torch.rand(att.shape, generator=tg) >= p).float()
+        masks.append(keep)
+        return att * keep / (1.0 - p)
+    gat_ref.F = types.SimpleNamespace(softmax=Fn.softmax, dropout=pinned_dropout, leaky_relu=Fn.leaky_relu)
+    xs = torch.randn(50, 64, generator=tg) * 0.7 + 0.2
+    out["gat/stats_x"], out["gat/stats_f"] = _np(xs), _np(gat_ref.extract_features(xs))
+    for tag, N, fin, fout, p, training in (("gat_layer_eval", 12, 11, 20, 0.2, False), ("gat_layer_train", 40, 30, 50, 0.2, True)):
+        torch.manual_seed(8)
+        layer = gat_ref.GraphAttentionLayer(fin, fout, p, 0.1)
+        layer.train(training)
+        h = torch.randn(3, N, fin, generator=tg).requires_grad_()
+        adj = torch.eye(N).unsqueeze(0).repeat(3, 1, 1)
+        idx = torch.arange(N - 1)
+        adj[:, idx, idx + 1] = 1
+        adj[:, idx + 1, idx] = 1
+        wgt = torch.randn(3, N, fout, generator=tg)
+        del masks[:]
+        yl = layer(h, adj)
+        (yl * wgt).sum().backward()
+        for k, v in layer.state_dict().items():
+            out[f"{tag}/sd/{k}"] = _np(v)
+        out[f"{tag}/h"], out[f"{tag}/adj"], out[f"{tag}/w"], out[f"{tag}/y"], out[f"{tag}/dh"] = _np(h), _np(adj[0]), _np(wgt), _np(yl), _np(h.grad)
+        if training:
+            out[f"{tag}/keep"] = _np(masks[0])
+        for k, prm in layer.named_parameters():
+            out[f"{tag}/grad/{k}"] = _np(prm.grad)
+    cfg = dict(num_patch=40, patch_size=64, hidden_dim=[300, 200, 100], lstm_hidden_dim=[30, 20], dropout=0.2)
+    torch.manual_seed(9)
+    mdl = gat_ref.GAT_LSTM_model(**cfg)
+    for k, v in mdl.state_dict().items():
+        out[f"gatlstm/sd0/{k}"] = _np(v)
+    X = torch.rand(3, 2560, generator=tg)
+    yt = torch.rand(3, 1, generator=tg)
+    mdl.eval()
+    with torch.no_grad():
+        out["gatlstm/y_eval"] = _np(mdl(X))
+    mdl.train()
+    del masks[:]
+    pred = mdl(X)
+    torch.nn.functional.mse_loss(pred, yt).backward()
+    assert torch.isfinite(pred).all() and len(masks) == 3
+    out["gatlstm/X"], out["gatlstm/y"], out["gatlstm/y_train"] = _np(X), _np(yt), _np(pred)
+    for li, keep in enumerate(masks):
+        out[f"gatlstm/keep{li}"] = _np(keep)
+    for k, prm in mdl.named_parameters():
+        out[f"gatlstm/grad/{k}"] = _np(prm.grad)
+    gat_ref.F = Fn
     path = os.path.join(OUT, "aux_metrics_data.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
