@@ -229,6 +229,27 @@ class STMSGCN(ASTGCNN):
         self.hparams = hparams
 
 
+class HAGCN(Algorithm):
+    """reference algorithms.py:222-248: Adam + MSE + alpha * KL of the three SAGPool layers."""
+
+    def __init__(self, configs, hparams, device):
+        super().__init__(configs)
+        from .hagcn import HAGCN_model
+        self.model = HAGCN_model(**configs)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
+                                          weight_decay=hparams["weight_decay"])
+        self.hparams = hparams
+        self.alpha = hparams["alpha"]
+
+    def update(self, X, y, epoch=None):
+        pred, kl = self.model(X, train=True)
+        loss = self.mse(pred, y) + self.alpha * kl
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return {"loss": loss.item()}
+
+
 class GAT_LSTM(ASTGCNN):
     """reference algorithms.py class GAT_LSTM: same update rule around GAT_LSTM_model (gat_lstm.py)."""
 
@@ -242,4 +263,4 @@ class GAT_LSTM(ASTGCNN):
 
 
 _ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN, "ST_GCN": ST_GCN, "STGNN": STGNN, "STMSGCN": STMSGCN,
-               "GAT_LSTM": GAT_LSTM}
+               "GAT_LSTM": GAT_LSTM, "HAGCN": HAGCN}

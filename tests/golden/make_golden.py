@@ -340,6 +340,31 @@ def aux_golden():
     for k, prm in mdl.named_parameters():
         out[f"gatlstm/grad/{k}"] = _np(prm.grad)
     gat_ref.F = Fn
+    # HAGCN (BASELINE configs[4], C-MAPSS hparams): whole reference model, train=True (prediction + KL term),
+    # the two active encoder dropouts pinned
+    from models.HAGCN.Model import HAGCN_model                       # noqa: E402
+    for tag, cfg, xshape in (("hagcn_p10", dict(patch_size=10, num_patch=5, encoder_hidden_dim=60, hidden_dim=64, output_dim=32), (4, 14, 50)),):
+        torch.manual_seed(10)
+        mdl = HAGCN_model(**cfg)
+        for k, v in mdl.state_dict().items():
+            out[f"{tag}/sd0/{k}"] = _np(v)
+        X = torch.rand(*xshape, generator=tg)
+        yt = torch.rand(xshape[0], 1, generator=tg)
+        mdl.eval()
+        with torch.no_grad():
+            out[f"{tag}/y_eval"] = _np(mdl(X))
+        mdl.train()
+        bsn, tl = xshape[0] * xshape[1], cfg["num_patch"]
+        keeps = [(torch.rand(tl, bsn, 120, generator=tg) >= 0.2).float(), (torch.rand(tl, bsn, 60, generator=tg) >= 0.2).float()]
+        mdl.TD.drop2, mdl.TD.drop3 = PinnedDropout(keeps[0], 0.2), PinnedDropout(keeps[1], 0.2)
+        pred, kl = mdl(X, train=True)
+        (torch.nn.functional.mse_loss(pred, yt) + 100.0 * kl).backward()
+        assert torch.isfinite(pred).all() and torch.isfinite(kl)
+        out[f"{tag}/X"], out[f"{tag}/y"], out[f"{tag}/y_train"], out[f"{tag}/kl"] = _np(X), _np(yt), _np(pred), _np(kl)
+        out[f"{tag}/keep0"], out[f"{tag}/keep1"] = _np(keeps[0]).astype(np.uint8), _np(keeps[1]).astype(np.uint8)
+        for k, prm in mdl.named_parameters():
+            if prm.grad is not None:
+                out[f"{tag}/grad/{k}"] = _np(prm.grad)
     path = os.path.join(OUT, "aux_metrics_data.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
