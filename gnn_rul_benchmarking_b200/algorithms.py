@@ -250,6 +250,18 @@ class HAGCN(Algorithm):
         return {"loss": loss.item()}
 
 
+class SAGCN(ASTGCNN):
+    """reference algorithms.py class SAGCN: same update rule around SAGCN_model (sagcn.py)."""
+
+    def __init__(self, configs, hparams, device):
+        Algorithm.__init__(self, configs)
+        from .sagcn import SAGCN_model
+        self.model = SAGCN_model(**configs)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
+                                          weight_decay=hparams["weight_decay"])
+        self.hparams = hparams
+
+
 class GAT_LSTM(ASTGCNN):
     """reference algorithms.py class GAT_LSTM: same update rule around GAT_LSTM_model (gat_lstm.py)."""
 
@@ -263,4 +275,4 @@ class GAT_LSTM(ASTGCNN):
 
 
 _ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN, "ST_GCN": ST_GCN, "STGNN": STGNN, "STMSGCN": STMSGCN,
-               "GAT_LSTM": GAT_LSTM, "HAGCN": HAGCN}
+               "GAT_LSTM": GAT_LSTM, "HAGCN": HAGCN, "SAGCN": SAGCN}

@@ -79,10 +79,64 @@ __global__ void __launch_bounds__(256) k_patch_stats11(const float* __restrict__
     o[7] = ma / rms; o[8] = ma / rsa; o[9] = rms / mabs; o[10] = ma / mabs;
   }
 }
+
+// extract_temporal_features, models/SAGCN/Model.py:21-38 (also AGCN_TF) -- 12 statistics per patch:
+//   max, min, std (unbiased), rms, mean, ptp, var (unbiased), entropy of softmax(x), std(asin(clamp(x))),
+//   std(atan(x)), kurtosis mean(d^4)/std^4 - 3, skewness mean(d^3)/std^3.
+__global__ void __launch_bounds__(256) k_patch_stats12(const float* __restrict__ x, long long R, int P,
+                                                       float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float* xr = x + row * P;
+  float mx = -INFINITY, mn = INFINITY, s = 0.f, sq = 0.f, sas = 0.f, sat = 0.f;
+  for (int i = lane; i < P; i += 32) {
+    const float v = xr[i];
+    mx = fmaxf(mx, v); mn = fminf(mn, v);
+    s += v; sq = fmaf(v, v, sq);
+    sas += asinf(fminf(fmaxf(v, -0.9999999f), 0.9999999f));
+    sat += atanf(v);
+  }
+  mx = warp_max(mx); mn = -warp_max(-mn);
+  s = warp_sum(s); sq = warp_sum(sq); sas = warp_sum(sas); sat = warp_sum(sat);
+  const float m = (float)P, mean = s / m, mas = sas / m, mat = sat / m;
+  float m2 = 0.f, m3 = 0.f, m4 = 0.f, vas = 0.f, vat = 0.f, se = 0.f;
+  for (int i = lane; i < P; i += 32) {
+    const float v = xr[i], d = v - mean, d2 = d * d;
+    m2 += d2; m3 = fmaf(d2, d, m3); m4 = fmaf(d2, d2, m4);
+    const float da = asinf(fminf(fmaxf(v, -0.9999999f), 0.9999999f)) - mas, dt = atanf(v) - mat;
+    vas = fmaf(da, da, vas); vat = fmaf(dt, dt, vat);
+    se += expf(v - mx);
+  }
+  m2 = warp_sum(m2); m3 = warp_sum(m3); m4 = warp_sum(m4);
+  vas = warp_sum(vas); vat = warp_sum(vat); se = warp_sum(se);
+  // entropy = -sum p log p with log p_i = x_i - mx - log(se)
+  const float lse = logf(se);
+  float ent = 0.f;
+  for (int i = lane; i < P; i += 32) {
+    const float lp = xr[i] - mx - lse;
+    ent = fmaf(-expf(lp), lp, ent);
+  }
+  ent = warp_sum(ent);
+  if (lane == 0) {
+    const float var = m2 / (m - 1.f), sd = sqrtf(var);
+    float* o = out + row * 12;
+    o[0] = mx; o[1] = mn; o[2] = sd; o[3] = sqrtf(sq / m); o[4] = mean; o[5] = mx - mn; o[6] = var; o[7] = ent;
+    o[8] = sqrtf(vas / (m - 1.f)); o[9] = sqrtf(vat / (m - 1.f));
+    o[10] = (m4 / m) / (sd * sd * sd * sd) - 3.f; o[11] = (m3 / m) / (sd * sd * sd);
+  }
+}
 }  // namespace
 }  // namespace stg
 
 using namespace stg;
+
+extern "C" int stg_patch_stats12(const float* x_dev, int64_t R, int P, float* out_dev, void* stream) {
+  if (!x_dev || !out_dev || R < 1 || P < 2) return set_err(STG_ERR_INVALID, "bad argument (patches need >= 2 samples)");
+  const long long grid = (R + 7) / 8;
+  k_patch_stats12<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x_dev, (long long)R, P, out_dev);
+  return check_cuda("stg_patch_stats12");
+}
 
 extern "C" int stg_patch_stats11(const float* x_dev, int64_t R, int P, float* out_dev, void* stream) {
   if (!x_dev || !out_dev || R < 1 || P < 4) return set_err(STG_ERR_INVALID, "bad argument (patches need >= 4 samples)");

@@ -183,6 +183,18 @@ def extract_features(data: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def extract_temporal_features(signals: torch.Tensor) -> torch.Tensor:
+    """models/SAGCN/Model.py:21-38: signals [rows, patch_size] -> [rows, 12] statistics (forward only)."""
+    if not signals.is_cuda:
+        raise RuntimeError("patch statistics run on the device (no CPU fallback)")
+    x = signals.detach().contiguous().float()
+    R, P = x.shape
+    out = torch.empty(R, 12, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().stg_patch_stats12(x.data_ptr(), R, P, out.data_ptr(), _stream()), "stg_patch_stats12")
+    return out
+
+
 class _GatAttention(torch.autograd.Function):
     """stg_gat_forward / stg_gat_backward: everything of GraphAttentionLayer.forward after its nn.Linear."""
 

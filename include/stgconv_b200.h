@@ -265,6 +265,9 @@ int stg_patch_stats(const float* x_dev, int64_t R, int P, float* out_dev, void* 
  * (mean sqrt|x|)^2, rms, (max-min)/2, skewness, kurtosis (the reference's sample-size coefficients), crest,
  * clearance, shape and impulse factors.  Forward only. */
 int stg_patch_stats11(const float* x_dev, int64_t R, int P, float* out_dev, void* stream);
+/* extract_temporal_features (models/SAGCN/Model.py:21-38): x [R, P] -> out [R, 12] = max, min, std, rms, mean,
+ * ptp, var, softmax entropy, std(asin(clamp x)), std(atan x), excess kurtosis, skewness.  Forward only. */
+int stg_patch_stats12(const float* x_dev, int64_t R, int P, float* out_dev, void* stream);
 
 /* Dense graph attention (primitive M5): GraphAttentionLayer.forward after its nn.Linear
  * (models/GAT_LSTM/Model.py:87-109).  Wh [G,N,F]; att_w [2F], att_b [1] = GraphAttentionLayer.attention;

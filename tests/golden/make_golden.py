@@ -365,6 +365,26 @@ def aux_golden():
         for k, prm in mdl.named_parameters():
             if prm.grad is not None:
                 out[f"{tag}/grad/{k}"] = _np(prm.grad)
+    # SAGCN (PHM2012 hparams: 160 patches of 16 samples): feature extraction and the whole reference model
+    import models.SAGCN.Model as sag_ref                            # noqa: E402
+    xs = torch.randn(60, 16, generator=tg) * 0.6
+    out["sagcn/stats_x"], out["sagcn/stats_t"] = _np(xs), _np(sag_ref.extract_temporal_features(xs))
+    out["sagcn/stats_f"] = _np(sag_ref.extract_frequency_features(xs))
+    cfg = dict(num_patch=160, patch_size=16, gcn_hidden_dim=100, attention_hidden_dim=100)
+    torch.manual_seed(12)
+    mdl = sag_ref.SAGCN_model(**cfg)
+    for k, v in mdl.state_dict().items():
+        out[f"sagcn/sd0/{k}"] = _np(v)
+    X = torch.randn(3, 2560, generator=tg) * 0.5
+    yt = torch.rand(3, 1, generator=tg)
+    mdl.train()
+    out["sagcn/feat"] = _np(sag_ref.extract_features(X.reshape(3, 160, 16)))
+    pred = mdl(X)
+    torch.nn.functional.mse_loss(pred, yt).backward()
+    assert torch.isfinite(pred).all()
+    out["sagcn/X"], out["sagcn/y"], out["sagcn/y_train"] = _np(X), _np(yt), _np(pred)
+    for k, prm in mdl.named_parameters():
+        out[f"sagcn/grad/{k}"] = _np(prm.grad)
     path = os.path.join(OUT, "aux_metrics_data.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
