@@ -172,106 +172,142 @@ class FC_STGNN(Algorithm):
         return {"loss": self.step(X, y).item()}
 
 
-class ASTGCNN(Algorithm):
-    """algorithms.py:139-163: Adam(lr, weight_decay) + MSE around ASTGCNN_model (native TCN / adjacency /
-    Chebyshev aggregation, see astgcnn.py)."""
+class _ModelAlgorithm(Algorithm):
+    """Common shape of the reference's other Algorithm subclasses (algorithms.py:139-163 and its clones):
+    `self.model = <Model>(**configs)`, `torch.optim.Adam(lr, weight_decay)`, `update` = forward -> loss ->
+    zero_grad -> backward -> step -> {'loss': loss.item()}.  Subclasses name the model class and may override
+    `_loss`.
+
+    `enable_cuda_graph(X, y)` captures that whole update (model forward with the library's kernels, autograd
+    backward, Adam) for batches of X's shape into one CUDA graph; later `update` calls with that shape copy the
+    batch into the graph's input buffers and replay it.  These models are small and launch-bound in eager mode, so
+    the replay is what a training loop should use.  Parameters, buffers and optimizer state are snapshotted before the
+    warm-up / capture and restored afterwards: enabling the graph does not change training."""
+
+    MODEL = None            # (module name, class name)
 
     def __init__(self, configs, hparams, device):
         super().__init__(configs)
-        from .astgcnn import ASTGCNN_model
-        self.model = ASTGCNN_model(**configs)
+        import importlib
+        mod, cls = self.MODEL
+        self.model = getattr(importlib.import_module("." + mod, __package__), cls)(**configs)
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
-                                          weight_decay=hparams["weight_decay"], fused=None)
+                                          weight_decay=hparams["weight_decay"])
         self.hparams = hparams
+        self._graph = None
 
-    def update(self, X, y, epoch=None):
-        loss = self.mse(self.model(X), y)
+    def _loss(self, X, y):
+        return self.mse(self.model(X), y)
+
+    def _eager_update(self, X, y):
+        loss = self._loss(X, y)
         self.optimizer.zero_grad()
         loss.backward()
         self.optimizer.step()
-        return {"loss": loss.item()}
+        return loss
+
+    def update(self, X, y, epoch=None):
+        if self._graph is not None and self.training and X.shape == self._gX.shape:
+            self._gX.copy_(X, non_blocking=True)
+            self._gy.copy_(y.reshape(self._gy.shape), non_blocking=True)
+            self._graph.replay()
+            return {"loss": self._gloss.item()}
+        return {"loss": self._eager_update(X, y).item()}
+
+    def enable_cuda_graph(self, X, y):
+        params = [p for p in self.model.parameters()]
+        dev = params[0].device
+        hp = self.hparams
+        old = self.optimizer.state_dict()
+        # graph-capturable Adam (step counter on the device); carries over any state accumulated so far
+        self.optimizer = torch.optim.Adam(params, lr=hp["learning_rate"], weight_decay=hp["weight_decay"], capturable=True)
+        if old["state"]:
+            for st in old["state"].values():
+                if not torch.is_tensor(st["step"]) or st["step"].device != dev:
+                    st["step"] = torch.as_tensor(float(st["step"]), dtype=torch.float32, device=dev)
+            self.optimizer.load_state_dict(old)
+            for grp in self.optimizer.param_groups:          # load_state_dict brought the old (eager) flag back
+                grp["capturable"] = True
+        self._gX, self._gy = X.detach().clone(), y.detach().clone()
+        snap_m = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        had_state = bool(old["state"])
+        snap_o = None
+        if had_state:
+            snap_o = [{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.optimizer.state[p].items()}
+                      for p in params]
+        was_training = self.training
+        self.train()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.optimizer.zero_grad(set_to_none=True)
+                self._loss(self._gX, self._gy).backward()
+                self.optimizer.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            self._gloss = self._loss(self._gX, self._gy)
+            self._gloss.backward()
+            self.optimizer.step()
+        with torch.no_grad():                       # undo the warm-up steps: weights, buffers, Adam moments
+            sd = self.model.state_dict()
+            for k, v in snap_m.items():
+                sd[k].copy_(v)
+            for i, p in enumerate(params):
+                st = self.optimizer.state[p]
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        v.copy_(snap_o[i][k]) if had_state else v.zero_()
+        self.train(was_training)
+        self._graph = graph
+
+    def disable_cuda_graph(self):
+        self._graph = None
 
 
-class ST_GCN(ASTGCNN):
-    """algorithms.py:465-491: same update rule around ST_GCN_model (native statistics / Pearson adjacency /
-    aggregation / TCN, see st_gcn.py)."""
+class ASTGCNN(_ModelAlgorithm):
+    """algorithms.py:139-163 around ASTGCNN_model (native TCN / adjacency / Chebyshev aggregation, astgcnn.py)."""
+    MODEL = ("astgcnn", "ASTGCNN_model")
+
+
+class ST_GCN(_ModelAlgorithm):
+    """algorithms.py:465-491 around ST_GCN_model (native statistics / Pearson adjacency / aggregation / TCN, st_gcn.py)."""
+    MODEL = ("st_gcn", "ST_GCN_model")
+
+
+class STGNN(_ModelAlgorithm):
+    """reference class STGNN around STGNN_model (stgnn.py)."""
+    MODEL = ("stgnn", "STGNN_model")
+
+
+class STMSGCN(_ModelAlgorithm):
+    """reference class STMSGCN around STMSGCN_model (stgnn.py)."""
+    MODEL = ("stgnn", "STMSGCN_model")
+
+
+class SAGCN(_ModelAlgorithm):
+    """reference class SAGCN around SAGCN_model (sagcn.py)."""
+    MODEL = ("sagcn", "SAGCN_model")
+
+
+class GAT_LSTM(_ModelAlgorithm):
+    """reference class GAT_LSTM around GAT_LSTM_model (gat_lstm.py)."""
+    MODEL = ("gat_lstm", "GAT_LSTM_model")
+
+
+class HAGCN(_ModelAlgorithm):
+    """algorithms.py:222-248: Adam + MSE + alpha * KL of the three SAGPool layers, around HAGCN_model (hagcn.py)."""
+    MODEL = ("hagcn", "HAGCN_model")
 
     def __init__(self, configs, hparams, device):
-        Algorithm.__init__(self, configs)
-        from .st_gcn import ST_GCN_model
-        self.model = ST_GCN_model(**configs)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
-                                          weight_decay=hparams["weight_decay"])
-        self.hparams = hparams
-
-
-class STGNN(ASTGCNN):
-    """reference algorithms.py class STGNN: same update rule around STGNN_model (stgnn.py)."""
-
-    def __init__(self, configs, hparams, device):
-        Algorithm.__init__(self, configs)
-        from .stgnn import STGNN_model
-        self.model = STGNN_model(**configs)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
-                                          weight_decay=hparams["weight_decay"])
-        self.hparams = hparams
-
-
-class STMSGCN(ASTGCNN):
-    """reference algorithms.py class STMSGCN: same update rule around STMSGCN_model (stgnn.py)."""
-
-    def __init__(self, configs, hparams, device):
-        Algorithm.__init__(self, configs)
-        from .stgnn import STMSGCN_model
-        self.model = STMSGCN_model(**configs)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
-                                          weight_decay=hparams["weight_decay"])
-        self.hparams = hparams
-
-
-class HAGCN(Algorithm):
-    """reference algorithms.py:222-248: Adam + MSE + alpha * KL of the three SAGPool layers."""
-
-    def __init__(self, configs, hparams, device):
-        super().__init__(configs)
-        from .hagcn import HAGCN_model
-        self.model = HAGCN_model(**configs)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
-                                          weight_decay=hparams["weight_decay"])
-        self.hparams = hparams
+        super().__init__(configs, hparams, device)
         self.alpha = hparams["alpha"]
 
-    def update(self, X, y, epoch=None):
+    def _loss(self, X, y):
         pred, kl = self.model(X, train=True)
-        loss = self.mse(pred, y) + self.alpha * kl
-        self.optimizer.zero_grad()
-        loss.backward()
-        self.optimizer.step()
-        return {"loss": loss.item()}
-
-
-class SAGCN(ASTGCNN):
-    """reference algorithms.py class SAGCN: same update rule around SAGCN_model (sagcn.py)."""
-
-    def __init__(self, configs, hparams, device):
-        Algorithm.__init__(self, configs)
-        from .sagcn import SAGCN_model
-        self.model = SAGCN_model(**configs)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
-                                          weight_decay=hparams["weight_decay"])
-        self.hparams = hparams
-
-
-class GAT_LSTM(ASTGCNN):
-    """reference algorithms.py class GAT_LSTM: same update rule around GAT_LSTM_model (gat_lstm.py)."""
-
-    def __init__(self, configs, hparams, device):
-        Algorithm.__init__(self, configs)
-        from .gat_lstm import GAT_LSTM_model
-        self.model = GAT_LSTM_model(**configs)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=hparams["learning_rate"],
-                                          weight_decay=hparams["weight_decay"])
-        self.hparams = hparams
+        return self.mse(pred, y) + self.alpha * kl
 
 
 _ALGORITHMS = {"FC_STGNN": FC_STGNN, "ASTGCNN": ASTGCNN, "ST_GCN": ST_GCN, "STGNN": STGNN, "STMSGCN": STMSGCN,

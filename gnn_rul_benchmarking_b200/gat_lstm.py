@@ -49,20 +49,18 @@ class GAT_LSTM_model(nn.Module):
         self.lstm_layers = nn.ModuleList([nn.LSTM(lstm_hidden_dim[i], lstm_hidden_dim[i + 1], num_layers=1, batch_first=True)
                                           for i in range(len(lstm_hidden_dim) - 1)])
         self.fc = nn.Linear(lstm_hidden_dim[-1] * num_patch, 1)
-
-    def path_adjacency(self, device):
-        """Model.py:144-148: identity + first off-diagonals (path graph over the patches); one [N,N] for all graphs."""
-        n = self.num_patch
-        adj = torch.eye(n, device=device)
-        idx = torch.arange(n - 1, device=device)
+        # Model.py:144-148: identity + first off-diagonals (path graph over the patches).  Constant, so it is
+        # built once (one [N,N] for all graphs; not part of the state dict, like the reference's local tensor)
+        adj = torch.eye(num_patch)
+        idx = torch.arange(num_patch - 1)
         adj[idx, idx + 1] = 1
         adj[idx + 1, idx] = 1
-        return adj
+        self.register_buffer("path_adj", adj, persistent=False)
 
     def forward(self, x):
         bs = x.size(0)
         x = extract_features(x.reshape(bs * self.num_patch, self.patch_size)).reshape(bs, self.num_patch, -1)
-        adj = self.path_adjacency(x.device)
+        adj = self.path_adj
         for gat in self.gat_layers:
             x = gat(x, adj)
         for lstm in self.lstm_layers:

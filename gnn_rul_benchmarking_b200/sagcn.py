@@ -26,7 +26,7 @@ def extract_frequency_features(signals, fs=1.0):
     broken towards the lower index (stable sort, first maximum), which is what the reference's CPU run does for the
     patch sizes it configures."""
     n = signals.shape[-1]
-    freqs = torch.fft.fftfreq(n, d=1 / fs).to(signals.device)
+    freqs = torch.fft.fftfreq(n, d=1 / fs, device=signals.device)
     fft_vals = torch.fft.fft(signals, dim=-1)
     amp = torch.abs(fft_vals)
     psd = amp ** 2 / n

@@ -83,3 +83,33 @@ def test_algorithm_update_runs(name, tag):
     for _ in range(20):
         l1 = alg.update(X, y, 1)["loss"]
     assert np.isfinite(l1) and l1 < l0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,tag", [("STGNN", "stgnn_nc"), ("STMSGCN", "stmsgcn")])
+def test_cuda_graph_update_matches_eager(name, tag):
+    """_ModelAlgorithm.enable_cuda_graph: the captured update (forward + backward + Adam) replays to the same
+    parameters as the eager update, and enabling it leaves the training state untouched."""
+    from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.allow_tf32 = False
+    hp = {"learning_rate": 1e-3, "weight_decay": 1e-4}
+    X, y = torch.from_numpy(Z[f"{tag}/X"]).to(dev), torch.from_numpy(Z[f"{tag}/y"]).to(dev)
+    algs = []
+    for _ in range(2):
+        a = get_algorithm_class(name)(CFG[tag][1], hp, dev)
+        a.model.load_state_dict(_sub(tag, "sd0"), strict=True)
+        algs.append(a.to(dev).train())
+    eager, graphed = algs
+    eager.update(X, y, 1)                         # one eager step on both first: the optimizer state carries over
+    graphed.update(X, y, 1)
+    before = {k: v.clone() for k, v in graphed.model.state_dict().items()}
+    graphed.enable_cuda_graph(X, y)
+    for k, v in graphed.model.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    for _ in range(4):
+        le = eager.update(X * 0.9, y, 1)["loss"]
+        lg = graphed.update(X * 0.9, y, 1)["loss"]
+    assert abs(le - lg) < 1e-5 * max(1.0, abs(le))
+    for (k, p), q in zip(eager.model.named_parameters(), graphed.model.parameters()):
+        assert _rel(q.detach().cpu(), p.detach().cpu()) < 2e-5, k
