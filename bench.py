@@ -113,7 +113,30 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
 
+    def _run_nvml(self):
+        """NVML directly (a sample every few ms: the timed region is only tens of ms long)."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = (("hw_slowdown", int(getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8))),
+                ("hw_thermal_slowdown", int(getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40))),
+                ("sw_thermal_slowdown", int(getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20))),
+                ("sw_power_cap", int(getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4))))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+            self._stop.wait(0.005)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
