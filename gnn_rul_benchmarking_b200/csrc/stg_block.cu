@@ -66,6 +66,9 @@ __global__ void __launch_bounds__(256) k_xmoments(const float* __restrict__ x, i
 // shared-memory carve-up common to the forward / backward main kernels
 // ------------------------------------------------------------------------------------------
 // window scratch; in the backward kernel it is re-used for the [CPH][CP]+[CPH] parameter-gradient tile
+// backward kernel: pack the windows' threads back to back instead of one warp-aligned slot per window?
+__host__ __device__ inline bool bwd_packed(int M) { return M > 32 && (M & 31) != 0; }
+
 __host__ __device__ inline int sb_floats(int wpc, int slot, int CP, int CPH, bool bwd) {
   int n = wpc * slot;
   if (bwd && n < CPH * CP + CPH) n = CPH * CP + CPH;
@@ -650,9 +653,12 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
   compute_fv<CP, HP>(sm, xs, rows, C);
   __syncthreads();
 
-  // one window per slot of ST = roundup32(M) threads: the phases of a window are separated by
-  // slot-local barriers (__syncwarp / named barrier), not CTA-wide ones
-  const int ST = ((M + 31) / 32) * 32;
+  // one window per slot of ST threads.  M <= 32 (and multiples of 32): ST = roundup32(M), the phases of a
+  // window are separated by slot-local barriers (__syncwarp / named barrier).  Otherwise (M = 40, 42: the 21-
+  // and 20-sensor shapes) a 64-thread slot would idle a third of its lanes, so the windows are packed back to
+  // back, ST = M, and the phases meet at a CTA barrier instead.
+  const bool packed = a.bwd_packed != 0;
+  const int ST = packed ? M : ((M + 31) / 32) * 32;
   const int slot_id = tid / ST, i = tid - slot_id * ST;
   const int ji = i / N, ni = i - ji * N;
   const bool lane_ok = slot_id < wpc && i < M;
@@ -662,7 +668,8 @@ __global__ void __launch_bounds__(256) k_block_bwd(const BlkArgs a, int rows_max
   float* dYs = sm.dYs + (size_t)sslot * M * HP;
   const float invw = 1.f / (float)w;
   auto slot_sync = [&]() {
-    if (ST == 32) __syncwarp();
+    if (packed) __syncthreads();
+    else if (ST == 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(slot_id + 1), "r"(ST) : "memory");
   };
   float dbt_acc[HP];
@@ -1098,8 +1105,13 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
     bool done = false;
     size_t cap0 = 74 * 1024;
     if (const char* e = getenv("STG_BWD_CAP_KB")) { const int v2 = atoi(e); if (v2 >= 16) cap0 = (size_t)v2 * 1024; }
+    const bool packed = bwd_packed(M) && !getenv("STG_BWD_NOPACK");
+    a.bwd_packed = packed ? 1 : 0;
+    // packed shapes: 6 windows of 40-42 nodes per CTA need ~100 KB; 2 CTAs/SM with full slots beat 3 with
+    // 4-window chunks (S2: 1085 -> 1012 us per step)
+    if (packed && !getenv("STG_BWD_CAP_KB")) cap0 = 113 * 1024;
     const size_t caps[2] = {cap0, kSmemCap};
-    const int ST = ((M + 31) / 32) * 32;           // threads per window slot in the backward kernel
+    const int ST = packed ? M : ((M + 31) / 32) * 32;     // threads per window slot in the backward kernel
     int wpc_b0 = 256 / ST;
     if (wpc_b0 < 1) wpc_b0 = 1;
     if (wpc_b0 > 15) wpc_b0 = 15;                   // named barriers 1..15
@@ -1121,7 +1133,7 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
         if (wmax > wp) continue;                        // a chunk would touch more windows than slots
         const size_t sm = carve_bytes(v->CP, v->HP, rows_max, a.C, wp, slot, M, true);
         if (sm <= caps[sweep]) {
-          p.wpc_b = wp; p.smem_b = sm; p.grid_x_b = gx; p.threads_b = wp * ST;
+          p.wpc_b = wp; p.smem_b = sm; p.grid_x_b = gx; p.threads_b = ((wp * ST + 31) / 32) * 32;
           done = true;
         }
       }

@@ -36,6 +36,7 @@ struct BlkArgs {
   // BN1 backward sums (k_block_bwd_stats), see stg_head.cu
   int head_fused;
   int prep_done;        // coefficient tables already written by k_xmoments_prep
+  int bwd_packed;       // k_block_bwd: windows' threads packed back to back (M = 40, 42 ...) instead of warp-aligned slots
   int fin_elsewhere;    // k_block_bwd_fin's work is done by the encoder's first backward phase
 };
 
