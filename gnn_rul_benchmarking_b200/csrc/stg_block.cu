@@ -1115,13 +1115,18 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
     int wpc_b0 = 256 / ST;
     if (wpc_b0 < 1) wpc_b0 = 1;
     if (wpc_b0 > 15) wpc_b0 = 15;                   // named barriers 1..15
+    // window passes per chunk (each pass = wp windows): more passes amortise the per-CTA prologue / epilogue and
+    // the duplicated boundary window over more windows, at the price of a larger slab.  Measured: worth it for the
+    // packed shapes (S2 1012 -> 945 us per step with 2), neutral or worse for M = 28.
+    int passes = packed ? 2 : 1;
+    if (const char* e = getenv("STG_BWD_PASSES")) { const int v2 = atoi(e); if (v2 >= 1 && v2 <= 8) passes = v2; }
     for (int sweep = 0; sweep < 2 && !done; ++sweep)
       for (int wp = wpc_b0; wp >= 1 && !done; --wp) {
         int gx = 0;
-        const int step_cap = wp + 1;                    // staged time steps of a stride-1, w=2 chunk
+        const int step_cap = passes * wp + 1;           // staged time steps of a stride-1, w=2 chunk
         for (int z = 0; z < a.nblk; ++z) {
           BlkDev& k = a.b[z];
-          int per = wp * k.stride - (k.w - 1);
+          int per = passes * wp * k.stride - (k.w - 1);
           if (per > step_cap - (k.w - 1) && step_cap - (k.w - 1) >= k.stride) per = step_cap - (k.w - 1);
           if (per < k.stride) per = k.stride;
           per = (per / k.stride) * k.stride;
@@ -1130,10 +1135,11 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
         }
         int wmax = 0;
         const int rows_max = bwd_rows_exact(a, &wmax);
-        if (wmax > wp) continue;                        // a chunk would touch more windows than slots
+        if (wmax > passes * wp) continue;               // a chunk would touch more windows than its passes hold
         const size_t sm = carve_bytes(v->CP, v->HP, rows_max, a.C, wp, slot, M, true);
         if (sm <= caps[sweep]) {
           p.wpc_b = wp; p.smem_b = sm; p.grid_x_b = gx; p.threads_b = ((wp * ST + 31) / 32) * 32;
+          if (p.threads_b < 64) p.threads_b = 64;       // the epilogue indexes up to C = 48 threads; surplus threads idle in the window loop
           done = true;
         }
       }
