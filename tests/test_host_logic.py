@@ -96,3 +96,28 @@ def test_flat_grad_allreduce_two_ranks_gloo():
         assert p.exitcode == 0
     assert n_ar == 3                                               # exactly one collective per backward
     assert torch.allclose(torch.tensor(params[0]), torch.tensor(params[1]), atol=1e-7)   # replicas stay identical
+
+
+def test_bench_reads_measured_peaks_in_any_documented_shape(tmp_path, monkeypatch):
+    """bench.py's roofline denominator: MEASURED_PEAKS.json `hbm_gbs` (flat or nested, sustained preferred),
+    else the profiling recipe's 6.65 TB/s fallback, and it says which."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.measured_peak_gbs() == (6650.0, "fallback")
+    (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"hbm_gbs": 6457.4, "bf16_tflops": 1590.0}))
+    assert bench.measured_peak_gbs() == (6457.4, "measured")
+    (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"hbm": {"burst_gbs": 6500.0, "sustained_gbs": 6300.0}}))
+    assert bench.measured_peak_gbs() == (6300.0, "measured")
+    (tmp_path / "MEASURED_PEAKS.json").write_text("not json")
+    assert bench.measured_peak_gbs() == (6650.0, "fallback")
+
+
+def test_sibling_algorithms_are_registered_with_reference_names():
+    from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
+    for name in ("FC_STGNN", "ASTGCNN", "ST_GCN", "STGNN", "STMSGCN", "GAT_LSTM", "HAGCN", "SAGCN"):
+        assert get_algorithm_class(name).__name__ == name
