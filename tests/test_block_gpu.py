@@ -131,6 +131,35 @@ def test_block_full_batch_properties():
     assert float((o1 - o2).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("N,C,H,stride", [(21, 14, 7, 1), (21, 14, 7, 2), (20, 16, 8, 1)])
+def test_backward_plans_agree_at_full_size(N, C, H, stride, monkeypatch):
+    """BASELINE full size (B=256, T=50) on the 42- / 40-node shapes: the default backward plan (windows packed back to
+    back, two passes per chunk) against the one-window-per-slot, one-pass plan -- same gradients up to summation order."""
+    from gnn_rul_benchmarking_b200.fc_stgnn import GraphConvpoolMPNN_block_v6
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    blk = GraphConvpoolMPNN_block_v6(C, H, N, 10, time_window_size=2, stride=stride, decay=0.7, pool_choice="mean").to(dev)
+    blk.train()
+    x = torch.randn(256, 50, N, C, device=dev)
+    L = (50 - 2) // stride + 1
+    dout = torch.randn(256, L, N, H, device=dev)
+    grads = []
+    for env in ({}, {"STG_BWD_NOPACK": "1", "STG_BWD_PASSES": "1"}):
+        for k in ("STG_BWD_NOPACK", "STG_BWD_PASSES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        blk.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        (blk(xg) * dout).sum().backward()
+        # (the theta bias is removed by BN1 in train mode: its gradient is pure cancellation noise, see the
+        #  properties test above, so it is left out of the comparison)
+        grads.append([("x", xg.grad.clone())] + [(k, p.grad.clone()) for k, p in blk.named_parameters()
+                                                  if k != "MPNN.theta.0.bias"])
+    for (k, a), (_, b) in zip(*grads):
+        assert _rel(a, b) < 2e-5, k
+
+
 def test_unsupported_shapes_raise():
     from gnn_rul_benchmarking_b200.fc_stgnn import GraphConvpoolMPNN_block_v6
     dev = torch.device("cuda:0")
