@@ -84,6 +84,17 @@ def test_invalid_arguments_return_status_not_crash():
     assert rc == -1
     with pytest.raises(ValueError):
         _lib.check(rc, "stg_model_forward")
+    # sibling primitives: null pointers / impossible sizes are status codes, unsupported tiles say so
+    assert lib.stg_patch_stats(None, 4, 16, None, None) == -1
+    assert lib.stg_patch_stats11(None, 4, 16, None, None) == -1
+    assert lib.stg_patch_stats12(None, 4, 16, None, None) == -1
+    assert lib.stg_gat_forward(None, None, None, None, 0, None, 0.0, 0.1, 0.01, 2, 8, 16, None, None) == -1
+    fake = C.c_void_p(256)                                           # never dereferenced: validation comes first
+    assert lib.stg_gat_forward(fake, fake, fake, fake, 0, None, 0.0, 0.1, 0.0, 2, 8, 16, fake, None) == -1      # slope 0
+    assert lib.stg_gat_forward(fake, fake, fake, fake, 0, None, 0.0, 0.1, 0.01, 2, 400, 400, fake, None) == -2  # tile
+    assert b"does not fit" in lib.stg_last_error()
+    assert lib.stg_adj_forward(9, fake, 2, 8, 4, 0, fake, None, None) == -1                                      # kind
+    assert lib.stg_agg_forward(0, fake, fake, 2, 400, 64, fake, None) == -2
 
 
 def test_product_package_never_imports_oracle():
