@@ -77,6 +77,7 @@ class FC_STGNN(Algorithm):
         hg = symm_mem.rendezvous(gsym, pg)
         flags = symm_mem.empty(64, dtype=torch.int32, device=dev)
         flags.zero_()
+        flags[34] = 1            # epoch of the flag protocol: monotonic, never restored (stg_p2p.cu)
         hf = symm_mem.rendezvous(flags, pg)
         eng.replace_grad_buffer(gsym)
         torch.cuda.synchronize(dev)
@@ -88,6 +89,13 @@ class FC_STGNN(Algorithm):
     def p2p_timed_out(self) -> bool:
         """True if a peer failed to show up inside the fused exchange kernel (bounded wait)."""
         return bool(getattr(self, "_p2p_flags", None) is not None and int(self._p2p_flags[33]) != 0)
+
+    def check_exchange(self) -> None:
+        """Raises if the fused NVLink exchange ever timed out on this rank (the kernel then skipped the
+        parameter update instead of applying a partial sum).  Synchronises the device."""
+        if self.p2p_timed_out():
+            raise RuntimeError("stg_allreduce_adam: a peer did not publish its gradients in time; "
+                               "the parameter update of that step was skipped on this rank")
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
     def enable_cuda_graph(self, batch_size):
@@ -116,6 +124,7 @@ class FC_STGNN(Algorithm):
                 self._eager_step(self._gX, self._gy)
         torch.cuda.current_stream(dev).wait_stream(side)
         self._hloss = torch.zeros(1, dtype=torch.float32).pin_memory()    # update()'s loss lands here
+        self._herr = torch.zeros(1, dtype=torch.int32).pin_memory()       # ... and the exchange's timeout word
         graph = torch.cuda.CUDAGraph()                  # step(): loss stays on the device
         with torch.cuda.graph(graph):
             self._gloss = self._eager_step(self._gX, self._gy)
@@ -123,6 +132,8 @@ class FC_STGNN(Algorithm):
         with torch.cuda.graph(graph_u):
             self._gloss_u = self._eager_step(self._gX, self._gy)
             self._hloss.copy_(self._gloss_u.reshape(1), non_blocking=True)
+            if getattr(self, "_dp_p2p", False):
+                self._herr.copy_(self._p2p_flags[33:34], non_blocking=True)
         with torch.no_grad():
             for t, s0 in zip((fl["param"], st["exp_avg"], st["exp_avg_sq"], st["step"]), snap):
                 t.copy_(s0)
@@ -168,8 +179,13 @@ class FC_STGNN(Algorithm):
             self._gy.copy_(y.reshape(self._gy.shape), non_blocking=True)
             self._graph_u.replay()
             torch.cuda.current_stream(self._gX.device).synchronize()
+            if int(self._herr[0]) != 0:
+                self.check_exchange()
             return {"loss": float(self._hloss[0])}
-        return {"loss": self.step(X, y).item()}
+        loss = self.step(X, y).item()
+        if getattr(self, "_dp_p2p", False):
+            self.check_exchange()
+        return {"loss": loss}
 
 
 class _ModelAlgorithm(Algorithm):

@@ -990,7 +990,25 @@ __global__ void __launch_bounds__(256) k_block_bwd_fin(const BlkArgs a, int CP) 
     for (int z = 0; z < a.nblk; ++z) {
       const float* tb = smf + z * per;
       float dv[4];
-      if (nv == 4) {
+      if (a.dxp_unfolded) {
+        // one row per (window, node): sum the (at most w) windows covering this time step
+        const BlkDev& k = a.b[z];
+        for (int u = 0; u < 4; ++u) {
+          dv[u] = 0.f;
+          if (u >= nv) continue;
+          const long long e = e0 + u;
+          const int c = (int)(e % C);
+          const long long r = e / C;
+          const int n = (int)(r % N);
+          const int t = (int)((r / N) % T);
+          const long long b = r / ((long long)N * T);
+          for (int j = 0; j < k.w; ++j) {
+            const int d = t - j;
+            if (d < 0 || d % k.stride || d / k.stride >= k.L) continue;
+            dv[u] += k.dxp[(((size_t)b * k.L + d / k.stride) * (k.w * N) + j * N + n) * C + c];
+          }
+        }
+      } else if (nv == 4) {
         const float4 v = *reinterpret_cast<const float4*>(a.b[z].dxp + e0);
         dv[0] = v.x; dv[1] = v.y; dv[2] = v.z; dv[3] = v.w;
       } else {
@@ -1074,7 +1092,8 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
   const int M = Mmax;
   if (M > 256) { snprintf(err, errlen, "w*N=%d nodes per graph > 256 unsupported", M); return -2; }
   p.CP = v->CP; p.HP = v->HP;
-  p.mma_f = 0; p.mma_b = 0; p.NT = 0;
+  p.mma_f = 0; p.mma_b = 0; p.NT = 0; p.tc = 0; p.tc_wr = 0;
+  a.dxp_unfolded = 0;
   const int slot = (M * (M + 1) > M * v->HP ? M * (M + 1) : M * v->HP);
   int wpc = 256 / M; if (wpc < 1) wpc = 1;
   // ---- forward: windows per chunk == windows in flight unless shared memory says otherwise
@@ -1147,6 +1166,11 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
   }
   // tensor-core backward is opt-in (STG_MMA_BWD=1): at 1 CTA/SM it does not beat the SIMT kernel yet
   if (!getenv("STG_NO_MMA") && getenv("STG_MMA_BWD")) plan_blocks_mma_bwd(a, p);
+  // Blackwell path: tcgen05.mma + TMEM for both directions whenever the shape fits (overrides the above)
+  if (plan_blocks_tc(a, p)) {
+    p.mma_f = 0; p.mma_b = 0;
+    a.dxp_unfolded = 1;
+  }
   return 0;
 }
 
@@ -1197,7 +1221,9 @@ int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
       ProfScope ps(kProfBlkPrep, s);
       k_block_prep<<<a.nblk, 256, 0, s>>>(a, p.CP, p.HP);
     }
-    if (p.mma_f) {
+    if (p.tc) {
+      launch_block_forward_tc(a, p, s);
+    } else if (p.mma_f) {
       launch_block_forward_mma(a, p, s);
     } else {
       ProfScope ps(kProfFwdMain, s);
@@ -1212,6 +1238,8 @@ int launch_block_forward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
       ProfScope ps(kProfFwdFin, s);
       k_block_fwd_fin<<<dim3((unsigned)((tot + 255) / 256), 1, a.nblk), 256, 0, s>>>(a);
     }
+  } else if (p.tc) {
+    launch_block_forward_tc(a, p, s);
   } else if (p.mma_f) {
     launch_block_forward_mma(a, p, s);
   } else {
@@ -1244,7 +1272,9 @@ int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
     ProfScope ps(kProfBwdStats, s);
     v->bwd_stats<<<dim3(g, 1, a.nblk), 256, 0, s>>>(a);
   }
-  if (p.mma_b) {
+  if (p.tc) {
+    launch_block_backward_tc(a, p, s);
+  } else if (p.mma_b) {
     launch_block_backward_mma(a, p, s);
   } else {
     ProfScope ps(kProfBwdMain, s);

@@ -38,11 +38,14 @@ struct BlkArgs {
   int prep_done;        // coefficient tables already written by k_xmoments_prep
   int bwd_packed;       // k_block_bwd: windows' threads packed back to back (M = 40, 42 ...) instead of warp-aligned slots
   int fin_elsewhere;    // k_block_bwd_fin's work is done by the encoder's first backward phase
+  int dxp_unfolded;     // tcgen05 backward: dxp holds one row per (window, node) [B, L, w*N, C]; the finalize folds it
 };
 
 struct BlkPlan {
   int CP, HP;           // padded feature dims the kernel template is instantiated for
-  int mma_f, mma_b;     // tensor-core path selected for forward / backward
+  int mma_f, mma_b;     // legacy mma.sync path selected for forward / backward
+  int tc, tc_wr;        // tcgen05 / TMEM path (stg_block_tc.cu) and its rows per window slot (32 or 64)
+  int tc_split;         // 3-term TF32 product for the projection / Gram / aggregation (see plan_blocks_tc)
   int NT;               // tensor-core path: 8-column tiles per graph (w*N <= 8*NT)
   int threads_f, threads_b;
   int wpc_f, wpc_b;     // windows processed concurrently per CTA
@@ -87,6 +90,11 @@ bool plan_blocks_mma_fwd(BlkArgs& a, BlkPlan& p);
 bool plan_blocks_mma_bwd(BlkArgs& a, BlkPlan& p);
 int launch_block_forward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
 int launch_block_backward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
+
+// tcgen05 / TMEM path (stg_block_tc.cu)
+bool plan_blocks_tc(BlkArgs& a, BlkPlan& p);
+int launch_block_forward_tc(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
+int launch_block_backward_tc(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
 
 // Launchers (enqueue only).
 int launch_xmoments(const float* x, int B, int T, int N, int C, double* xmom, cudaStream_t s);

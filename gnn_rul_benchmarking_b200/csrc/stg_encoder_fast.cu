@@ -372,7 +372,22 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
             const float* tb = stage + z * (4 * C + T);
             const float cn = tb[4 * C + t];
             float dv[C];
-            load_row<C>(a.fin.dxp[z] + (size_t)r * C, dv);
+            if (a.fin.unfolded) {
+              // sum the windows covering time step t (rows (l, j, n) with l*stride + j == t)
+#pragma unroll
+              for (int c = 0; c < C; ++c) dv[c] = 0.f;
+              const int Lz = a.fin.L[z], sz = a.fin.stride[z], wz = a.fin.w[z];
+              for (int j = 0; j < wz; ++j) {
+                const int d = t - j;
+                if (d < 0 || d % sz || d / sz >= Lz) continue;
+                float pv[C];
+                load_row<C>(a.fin.dxp[z] + ((((size_t)b * Lz + d / sz) * wz + j) * N + n) * C, pv);
+#pragma unroll
+                for (int c = 0; c < C; ++c) dv[c] += pv[c];
+              }
+            } else {
+              load_row<C>(a.fin.dxp[z] + (size_t)r * C, dv);
+            }
 #pragma unroll
             for (int c = 0; c < C; ++c) {
               const float xh = (xv[c] - tb[c]) * tb[C + c];

@@ -35,6 +35,7 @@ struct EncArgs {
   //   dh = sum_z dxp_z - r0_z*cnt_z(t)*(m1_z + xhat_z*m2_z), written to dh_out, BN0/BN1 affine gradients.
   struct Fin {
     int nblk, CP;
+    int unfolded;               // dxp has one row per (window, node): [B, L, w*N, C] (tcgen05 block backward)
     const float* dxp[2];        // [R, C] per block: dx before the BN0 mean terms
     const float* tab[2];        // block coefficient table: mu0[CP] r0[CP] ...
     const double* stats[2];     // block sums (see stg_block_desc.stats)

@@ -51,7 +51,11 @@ void layout(const stg_model_dims& d, const Geo& g, Ws& w) {
   w.feat = o; o += al((size_t)d.B * g.F * 4);
   w.dfeat = o; o += al((size_t)d.B * g.F * 4);
   for (int z = 0; z < 2; ++z) { w.yp[z] = o; o += al((size_t)d.B * g.L[z] * g.M[z] * d.H * 4); }
-  for (int z = 0; z < 2; ++z) { w.dxp[z] = o; o += rc; }
+  // dx partials: [B,T,N,C] (folded) or one row per (window, node) [B,L,w*N,C] on the tcgen05 path
+  for (int z = 0; z < 2; ++z) {
+    const size_t unf = al((size_t)d.B * g.L[z] * g.M[z] * g.C * 4);
+    w.dxp[z] = o; o += unf > rc ? unf : rc;
+  }
   w.d1 = o; o += al((size_t)d.B * g.J * 4);
   {
     const size_t tiles = ((size_t)g.R + 255) / 256;
@@ -170,7 +174,7 @@ int build_ctx(Ctx& c, const stg_model_dims* dp, const stg_model_params* pp, cons
   if (training && gp && encoder_fast_available(e)) {
     a.fin_elsewhere = 1;
     EncArgs::Fin& f = e.fin;
-    f.nblk = STG_MAX_BLOCKS; f.CP = c.plan.CP;
+    f.nblk = STG_MAX_BLOCKS; f.CP = c.plan.CP; f.unfolded = a.dxp_unfolded;
     for (int z = 0; z < STG_MAX_BLOCKS; ++z) {
       const BlkDev& k = a.b[z];
       f.dxp[z] = k.dxp; f.tab[z] = k.coef; f.stats[z] = k.stats; f.g0[z] = k.g0;

@@ -7,6 +7,10 @@
 //   4. applies torch.optim.Adam semantics (algorithms/algorithms.py:60-64) to the local parameters,
 //   5. publishes "done reading" and leaves only when every peer is done, so the next step may overwrite
 //      the gradient buffers.
+// The epoch of the flag protocol is a counter in the flag block itself (word 34, starts at 1, bumped by the
+// last block of every exchange): it only ever grows, independently of the Adam step, which a CUDA-graph
+// capture snapshots and restores.  A rank whose wait times out (about 2 s) raises word 33 and SKIPS the
+// parameter update; the host checks the word (FC_STGNN.update / check_exchange) and raises.
 // It replaces ncclAllReduce + k_adam (latency-bound at this size: ~45 us at 8 GPUs inside the step graph).
 // The peer pointers come from torch's symmetric-memory rendezvous on the host side (engine.py).
 #include <math.h>
@@ -20,7 +24,8 @@ namespace {
 constexpr int kMaxWorld = 16;
 struct P2PArgs {
   const float* grad[kMaxWorld];
-  unsigned* flags[kMaxWorld];      // per rank: [0,16) ready, [16,32) done, [32] block counter, [33] timeout flag
+  unsigned* flags[kMaxWorld];      // per rank: [0,16) ready, [16,32) done, [32] block counter, [33] timeout flag,
+                                   //           [34] epoch of the flag protocol (next exchange)
   int rank, world;
 };
 
@@ -48,13 +53,20 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(const P2PArgs pa, float*
   __shared__ float s_bc[2];
   __shared__ int s_last;
   const int tid = threadIdx.x, world = pa.world;
-  const unsigned epoch = (unsigned)(*step);
   unsigned* mine = pa.flags[pa.rank];
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(mine + 34);   // bumped by the last block only
+  __shared__ unsigned s_err;
+  if (tid == 0) s_err = 0u;
+  __syncthreads();
   if (blockIdx.x == 0 && tid < world) {
     __threadfence_system();                                  // gradients of the earlier kernels -> visible to peers
     st_release_sys(pa.flags[tid] + pa.rank, epoch);
   }
-  if (tid < world) wait_flag(mine + tid, epoch, mine + 33);
+  if (tid < world) {
+    unsigned err = 0u;
+    wait_flag(mine + tid, epoch, &err);
+    if (err) { mine[33] = 1u; s_err = 1u; }
+  }
   if (tid == 0) {
     const double t = (double)(*step);
     s_bc[0] = (float)(1.0 - pow((double)b1, t));
@@ -62,10 +74,12 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(const P2PArgs pa, float*
   }
   __syncthreads();
   const float bc1 = s_bc[0], bc2s = s_bc[1], step_size = lr / bc1, gscale = 1.f / (float)world;
+  // a peer that never showed up: leave the parameters alone (the host raises on word 33)
+  const bool skip = s_err != 0u || *reinterpret_cast<volatile unsigned*>(mine + 33) != 0u;
   float4* p4 = reinterpret_cast<float4*>(p);
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
-  for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n4; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n4 && !skip; i += (long long)gridDim.x * blockDim.x) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < world; ++r) {                        // rank order: identical sums on every replica
       const float4 q = __ldcv(reinterpret_cast<const float4*>(pa.grad[r]) + i);
@@ -93,8 +107,12 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(const P2PArgs pa, float*
   if (tid < world) {
     __threadfence_system();
     st_release_sys(pa.flags[tid] + 16 + pa.rank, epoch);    // "I am done reading your gradients"
-    wait_flag(mine + 16 + tid, epoch, mine + 33);           // nobody still reads mine
+    unsigned err = 0u;
+    wait_flag(mine + 16 + tid, epoch, &err);                // nobody still reads mine
+    if (err) mine[33] = 1u;
   }
+  __syncthreads();
+  if (tid == 0) mine[34] = epoch + 1u;                      // next exchange (stream order makes it visible)
 }
 
 }  // namespace
@@ -119,7 +137,7 @@ extern "C" int stg_allreduce_adam(float* param_dev, float* exp_avg_dev, float* e
   pa.rank = rank; pa.world = world;
   cudaStream_t s = (cudaStream_t)stream;
   long long* ctr[1] = {(long long*)step_dev};
-  launch_tick(ctr, 1, s);                                    // ++step (also the epoch of the flag protocol)
+  launch_tick(ctr, 1, s);                                    // ++step (Adam bias correction only)
   const long long n4 = n / 4;
   int grid = (int)((n4 + 255) / 256);
   if (grid > 132) grid = 132;                                // co-resident by a wide margin: blocks never wait on each other

@@ -117,7 +117,10 @@ class _GraphBlocks(torch.autograd.Function):
         Ftot = dfeat.shape[1]
         descs = (_lib.StgBlockDesc * nblk)()
         grads = (_lib.StgBlockGrads * nblk)()
-        dxp = torch.empty(nblk, B, T, N, Cc, device=x.device, dtype=torch.float32)
+        # per-block dx scratch: [B,T,N,C], or one row per (window, node) [B,L,w*N,C] on the tcgen05 path
+        # (STG_BLOCK_DXP_FLOATS in include/stgconv_b200.h)
+        dxp_floats = max(B * max(T * N, ((T - hp["w"]) // hp["stride"] + 1) * hp["w"] * N) * Cc for hp in hyper)
+        dxp = torch.empty(nblk, dxp_floats, device=x.device, dtype=torch.float32)
         dx = torch.empty_like(x)
         out_grads: List[torch.Tensor] = []
         off = 0

@@ -90,13 +90,20 @@ typedef struct stg_block_desc {
 #define STG_BLOCK_STATS_DOUBLES(C, H, T) \
   (((STG_BLOCK_SUMS_DOUBLES(C, H) + 1) / 2) * 2 + (STG_BLOCK_COEF_FLOATS(C, H, T) + 1) / 2)
 
+#define STG_BLOCK_DXP_FLOATS(B, T, N, C, w, stride)                                              \
+  ((size_t)(B) * (size_t)(C) *                                                                   \
+   ((size_t)(T) * (N) > (size_t)(((T) - (w)) / (stride) + 1) * (w) * (N)                         \
+        ? (size_t)(T) * (N)                                                                      \
+        : (size_t)(((T) - (w)) / (stride) + 1) * (w) * (N)))
+
 /* gradients of one block, device pointers; all are ACCUMULATED into (+=) except dxp. */
 typedef struct stg_block_grads {
   const float* dout;  /* [B,L,N,H], sample stride dout_bstride                              */
   int64_t dout_bstride;
   float* dWm; float* dbm; float* dbn0_w; float* dbn0_b;
   float* dWt; float* dbt; float* dbn1_w; float* dbn1_b;
-  float* dxp;         /* [B,T,N,C] scratch: this block's dx before the BN-0 mean terms      */
+  float* dxp;         /* scratch, STG_BLOCK_DXP_FLOATS floats: this block's dx before the BN-0 mean
+                         terms, [B,T,N,C] or one row per (window, node) [B,L,w*N,C] (tcgen05 path)  */
 } stg_block_grads;
 
 /* Per-time-step moments of x for the BatchNorm1d(C) of every block reading x:
@@ -293,9 +300,11 @@ int stg_metrics(const float* pred_dev, const float* real_dev, int64_t n, float m
 /* Data-parallel step (the reference has no distributed code): one-shot
  * all-reduce of the flat gradient buffers over NVLink peer memory fused with the Adam update.
  * grad_ptrs[r] / flag_ptrs[r] (host arrays of `world` device pointers) address rank r's gradient
- * buffer (n floats) and flag block (>= 64 zero-initialised uint32) and must be peer-mapped on this
- * device (e.g. torch symmetric memory).  Every rank must call it once per step with the same n;
- * the kernel waits (bounded, ~2 s) for all peers.  flag word 33 != 0 afterwards means a peer timed out. */
+ * buffer (n floats) and flag block (>= 64 uint32, all zero except word 34 = 1, the epoch of the flag
+ * protocol, which the kernel itself advances and which must never be rewound) and must be peer-mapped
+ * on this device (e.g. torch symmetric memory).  Every rank must call it once per step with the same n;
+ * the kernel waits (bounded, ~2 s) for all peers.  flag word 33 != 0 afterwards means a peer timed out;
+ * the rank that saw the timeout skipped its parameter update for that step. */
 int stg_allreduce_adam(float* param_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, int64_t* step_dev,
                        const float* const* grad_ptrs, uint32_t* const* flag_ptrs, int rank, int world, float lr,
                        float beta1, float beta2, float eps, float weight_decay, void* stream);

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q, p2p=False):
+def _worker(rank, world, port, q, p2p=False, graph=False):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -27,6 +27,8 @@ def _worker(rank, world, port, q, p2p=False):
     alg.train()
     alg.attach_data_parallel(p2p=p2p)
     assert alg._dp_p2p == bool(p2p)
+    if graph:          # the order bench.py uses: exchange attached first, then the step graph captured
+        alg.enable_cuda_graph(8)
     g = torch.Generator().manual_seed(3)
     X, y = torch.rand(16, 14, 50, generator=g), torch.rand(16, 1, generator=g)
     losses = []
@@ -58,11 +60,11 @@ def test_two_gpu_replicas_stay_identical():
     assert torch.equal(params[0], params[1])           # same averaged gradient -> same Adam update
 
 
-def _run(p2p):
+def _run(p2p, graph=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 2000) + (7 if p2p else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, p2p)) for r in range(2)]
+    port = 29700 + (os.getpid() % 2000) + (7 if p2p else 0) + (13 if graph else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, p2p, graph)) for r in range(2)]
     for p in procs:
         p.start()
     out = q.get(timeout=300)
@@ -82,3 +84,15 @@ def test_fused_nvlink_exchange_matches_nccl():
     assert torch.equal(p_p2p[0], p_p2p[1])             # replicas identical
     assert all(abs(a - b) < 1e-6 for a, b in zip(l_nccl, l_p2p))
     assert float((p_nccl[0] - p_p2p[0]).abs().max()) < 2e-6
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_fused_exchange_inside_cuda_graph_keeps_replicas_identical():
+    """attach_data_parallel(p2p) followed by enable_cuda_graph (bench.py's order): the capture's warm-up steps are
+    rolled back, the flag protocol's epoch is not -- the replayed steps must still wait for their peers.  Replicas
+    stay bit-identical, nobody times out, and the result equals the eager fused exchange."""
+    l_e, p_e = _run(True, graph=False)
+    l_g, p_g = _run(True, graph=True)
+    assert torch.equal(p_g[0], p_g[1])
+    assert all(abs(a - b) < 1e-6 for a, b in zip(l_e, l_g))
+    assert float((p_e[0] - p_g[0]).abs().max()) < 2e-6

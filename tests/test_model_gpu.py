@@ -6,12 +6,11 @@ import os
 import pytest
 import torch
 
-from conftest import golden_files, load_golden
+from conftest import (GRAD_TOL_FP32, GRAD_TOL_TC, OUT_TOL, assert_close_rel, assert_grads_close, golden_files,
+                      load_golden, tc_shape)
 from oracle import fc_stgnn_oracle as orc
 
 pytestmark = pytest.mark.gpu
-OUT_TOL = 2e-5      # contract: 1e-4 (BASELINE.json north_star)
-GRAD_TOL = 1e-4
 
 
 class PinnedDropout(torch.nn.Module):
@@ -21,10 +20,6 @@ class PinnedDropout(torch.nn.Module):
 
     def forward(self, x):
         return x * self.keep / (1.0 - self.p) if self.training else x
-
-
-def _rel(a, b):
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
 
 
 @pytest.mark.parametrize("path", golden_files("model"), ids=os.path.basename)
@@ -41,16 +36,17 @@ def test_model_matches_reference_golden(path):
     X, y = g["X"].to(dev), g["y"].to(dev)
     model.eval()
     with torch.no_grad():
-        assert _rel(model(X).cpu(), g["y_eval"]) < OUT_TOL
+        assert_close_rel(model(X).cpu(), g["y_eval"], OUT_TOL, "eval output")
     model.positional_encoding.dropout = PinnedDropout(g["keep"].float().to(dev), 0.1)
     model.train()
     pred = model(X)
-    assert _rel(pred.detach().cpu(), g["y_train"]) < OUT_TOL
+    assert_close_rel(pred.detach().cpu(), g["y_train"], OUT_TOL, "train output")
     loss = torch.nn.functional.mse_loss(pred, y)
     assert abs(float(loss) - float(g["loss"])) < 1e-5
     loss.backward()
-    for k, p in model.named_parameters():
-        assert _rel(p.grad.cpu(), g["grad"][k]) < GRAD_TOL, k
+    tol = GRAD_TOL_TC if tc_shape(2 * cfg["hidden_dim"], cfg["hidden_dim"], cfg["num_node"]) else GRAD_TOL_FP32
+    got = {k: p.grad.cpu() for k, p in model.named_parameters()}
+    assert_grads_close(got, {k: g["grad"][k] for k in got}, tol, g["name"])
     sd = model.state_dict()
     for k, ref in g["sd1"].items():
         assert torch.allclose(sd[k].cpu().to(ref.dtype), ref, atol=1e-5, rtol=1e-4), k
