@@ -23,6 +23,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # --use_fast_math would turn 1/sqrt and divisions into approximate forms; the kernels call
 # __expf explicitly where the approximation is intended, so it is NOT enabled:
 NVCC_FLAGS.remove("--use_fast_math")
+# debug builds only (e.g. STG_EXTRA_NVCC_FLAGS=-DSTG_TC_TIMING); part of the build stamp
+NVCC_FLAGS += os.environ.get("STG_EXTRA_NVCC_FLAGS", "").split()
 
 
 def nvcc_path() -> str:

@@ -50,7 +50,10 @@ void layout(const stg_model_dims& d, const Geo& g, Ws& w) {
   w.dh = o; o += rc;
   w.feat = o; o += al((size_t)d.B * g.F * 4);
   w.dfeat = o; o += al((size_t)d.B * g.F * 4);
-  for (int z = 0; z < 2; ++z) { w.yp[z] = o; o += al((size_t)d.B * g.L[z] * g.M[z] * d.H * 4); }
+  for (int z = 0; z < 2; ++z) {
+    w.yp[z] = o;
+    o += al(STG_BLOCK_SAVED_FLOATS(d.B, d.T, d.N, d.H, d.w[z], d.stride[z]) * 4);
+  }
   // dx partials: [B,T,N,C] (folded) or one row per (window, node) [B,L,w*N,C] on the tcgen05 path
   for (int z = 0; z < 2; ++z) {
     const size_t unf = al((size_t)d.B * g.L[z] * g.M[z] * g.C * 4);

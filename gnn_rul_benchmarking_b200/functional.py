@@ -45,6 +45,13 @@ def num_windows(T: int, w: int, s: int) -> int:
     return (T - w) // s + 1
 
 
+def saved_floats(windows: int, M: int, H: int) -> int:
+    """STG_BLOCK_SAVED_FLOATS (include/stgconv_b200.h): Y' rows, then the F | V rows and the softmax rows the
+    tcgen05 forward keeps for the backward."""
+    rows = windows * M
+    return (rows * H + 3) // 4 * 4 + rows * 24 + rows * (M + 1)
+
+
 class _GraphBlocks(torch.autograd.Function):
     """nblk GraphConvpoolMPNN_block_v6 instances reading the same x -> concatenated features."""
 
@@ -85,7 +92,7 @@ class _GraphBlocks(torch.autograd.Function):
                 d.out = feat.data_ptr() + 4 * off
                 d.out_bstride = Ftot
                 if training:
-                    yp = torch.empty(B, Ls[z], hp["w"] * N, hp["H"], device=x.device, dtype=torch.float32)
+                    yp = torch.empty(saved_floats(B * Ls[z], hp["w"] * N, hp["H"]), device=x.device, dtype=torch.float32)
                     st = torch.empty(stats_doubles(Cc, hp["H"], T), device=x.device, dtype=torch.float64)
                     d.yp, d.stats = yp.data_ptr(), st.data_ptr()
                     saved_yp.append(yp)

@@ -71,9 +71,16 @@ typedef struct stg_block_desc {
   /* outputs / saved-for-backward, device pointers */
   float* out;         /* [B, L, N, H] with sample stride out_bstride (floats)              */
   int64_t out_bstride;/* >= L*N*H; lets two blocks write straight into the FC-head input   */
-  float* yp;          /* training only: pre-BN Y' [B,L,w*N,H] (saved for backward)         */
+  float* yp;          /* training only: STG_BLOCK_SAVED_FLOATS floats saved for the backward:
+                         pre-BN Y' [B,L,w*N,H], then (tcgen05 path) the F | V rows [B*L*w*N, 24]
+                         and the softmax numerators [B*L, w*N + 1, w*N]                     */
   double* stats;      /* training only: STG_BLOCK_STATS_DOUBLES(C,H,T) doubles of scratch  */
 } stg_block_desc;
+
+#define STG_BLOCK_WINDOWS(T, w, stride) (((T) - (w)) / (stride) + 1)
+#define STG_BLOCK_SAVED_FLOATS(B, T, N, H, w, stride)                                            \
+  ((((size_t)(B) * STG_BLOCK_WINDOWS(T, w, stride) * (w) * (N) * (H) + 3) / 4) * 4 +             \
+   (size_t)(B) * STG_BLOCK_WINDOWS(T, w, stride) * (w) * (N) * (24 + (w) * (N) + 1))
 
 /* layout of stg_block_desc.stats (doubles):
  *   [0,H)        sum_R  Y'            [H,2H)      sum_R Y'^2          (forward)
