@@ -1,5 +1,6 @@
 // tcgen05 / TMEM graph-conv block, BACKWARD kernel (design notes: stg_tc.cuh; math: SURVEY.md section 9.2).
 // Reference: autograd through GraphConvpoolMPNN_block_v6.forward, models/FC_STGNN/Model_Base.py:190-225.
+#define STG_STAMP_KERNEL 1
 #include "stg_tc.cuh"
 
 namespace stg {
@@ -17,6 +18,9 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   const int cta = z == 0 ? blockIdx.x : blockIdx.x - ncta0;
   const int ncta = z == 0 ? ncta0 : gridDim.x - ncta0;
   const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef STG_TC_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][14] = clock64();
+#endif
   const int N = NT ? NT : a.N, M = 2 * N;
   const int C = a.C, T = a.T, H = k.H, s = k.stride, Lw = k.L;
   const long long nwin = (long long)a.B * Lw;
@@ -103,6 +107,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
     const long long g = (long long)tile * WPT + wl;
     const bool valid = row_ok && g < nwin;
     const size_t grow = (size_t)g * M + i;          // row of this thread in the [B*L*M, .] saved tensors
+    STG_STAMP(0)
     // ---- step 1: this row's x, saved F | V, saved softmax row, Y', dout -> dY'; operands of dA = dY' . V^T
     float dY[8];
     float es[WR];                                   // softmax numerators e_k of the row (sign bit: S > 0)
@@ -158,7 +163,9 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
     }
     fence_async_smem();
     tc_fence_before();
+    STG_STAMP(1)
     __syncthreads();
+    STG_STAMP(2)
     if (tid == 0) {
       tc_fence_after();
       constexpr uint32_t id = idesc_tf32(128, 0, 0);
@@ -166,8 +173,10 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
       mma_ss(tmem + regB, dsc(yk_lo, kHiK), dsc(yk_lo + 256, kHiK), id, 0);
       mma_commit(&ctl.bar);
     }
+    STG_STAMP(3)
     mbar_wait(&ctl.bar, ph); ph ^= 1;
     tc_fence_after();
+    STG_STAMP(4)
     // ---- step 5: softmax backward of the row (P and the sign of S come from the forward)
     {
       float da[WR];
@@ -219,7 +228,9 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
     }
     fence_async_smem();
     tc_fence_before();
+    STG_STAMP(5)
     __syncthreads();
+    STG_STAMP(6)
     if (tid == 0) {
       tc_fence_after();
       constexpr uint32_t id_ts = idesc_tf32(16, 0, 1);      // A from TMEM (K-major by construction), B MN-major
@@ -237,8 +248,10 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
       }
       mma_commit(&ctl.bar);
     }
+    STG_STAMP(7)
     mbar_wait(&ctl.bar, ph); ph ^= 1;
     tc_fence_after();
+    STG_STAMP(8)
     // ---- step 7: [dF | dV] rows -> MN-major records (parameter-gradient product) and K-major rows (+ residuals)
     //      for the dx projection
     {
@@ -261,7 +274,9 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
     }
     fence_async_smem();
     tc_fence_before();
+    STG_STAMP(9)
     __syncthreads();
+    STG_STAMP(10)
     if (tid == 0) {
       tc_fence_after();
       constexpr uint32_t id_x = idesc_tf32(16, 0, 0);       // dx partial: all 128 rows share [Wm ; a0 Wtheta]
@@ -279,8 +294,10 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
         mma_ss(tmem + regA + 64, dsc(t1g_lo + ks * 64, kHiMN), dsc(rb_lo + ks * 64, kHiMN), id_g, ks);
       mma_commit(&ctl.bar);
     }
+    STG_STAMP(11)
     mbar_wait(&ctl.bar, ph); ph ^= 1;
     tc_fence_after();
+    STG_STAMP(12)
     // ---- step 9: unfolded dx partial rows, parameter-gradient accumulators
     {
       float dx[16];
@@ -307,6 +324,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
       }
     }
     tc_fence_before();
+    STG_STAMP(13)
   }
 
   // ---- CTA epilogue: parameter gradients, BN0 backward sums, dbtheta
@@ -355,6 +373,9 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   if (tid < H) atomicAdd(&k.dbt[tid], red[24 * 17 + tid]);
   tc_fence_before();
   __syncthreads();
+#ifdef STG_TC_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][15] = clock64();
+#endif
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
@@ -372,6 +393,12 @@ static void launch_bwd(const BlkArgs& a, int total, int n0, size_t smem, cudaStr
 }
 
 }  // namespace tc
+
+#ifdef STG_TC_TIMING
+extern "C" int stg_debug_tc_stamps_bwd(long long* out32) {
+  return cudaMemcpyFromSymbol(out32, tc::g_tc_stamp, sizeof(long long) * 32) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int launch_block_backward_tc(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   using namespace tc;

@@ -1,18 +1,11 @@
 // tcgen05 / TMEM graph-conv block, FORWARD kernel (design notes: stg_tc.cuh).
 // Reference: GraphConvpoolMPNN_block_v6.forward, models/FC_STGNN/Model_Base.py:190-225.
+#define STG_STAMP_KERNEL 0
 #include "stg_tc.cuh"
 
 namespace stg {
 namespace tc {
 
-#ifdef STG_TC_TIMING
-// debug build only (-DSTG_TC_TIMING): clock64 stamps of CTA 0's second tile, threads 0 and 64
-__device__ long long g_tc_stamp[2][16];
-#define STG_STAMP(n)                                                                              \
-  if (blockIdx.x == 0 && tile == cta + ncta && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][n] = clock64();
-#else
-#define STG_STAMP(n)
-#endif
 
 // WR rows per window slot (32 / 64), NT = number of sensors N when known at compile time (0: runtime, N <= WR/2),
 // TRAIN: write pre-BN Y' and its batch moments (BN1 + leaky_relu + pooling are fused into the FC head) and save the
@@ -33,6 +26,9 @@ __global__ void __launch_bounds__(128, WR == 32 ? 4 : 2) k_block_fwd_tc(const Bl
   const int cta = z == 0 ? blockIdx.x : blockIdx.x - ncta0;
   const int ncta = z == 0 ? ncta0 : gridDim.x - ncta0;
   const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef STG_TC_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][14] = clock64();
+#endif
   const int N = NT ? NT : a.N, M = 2 * N;
   const int C = a.C, T = a.T, H = k.H, s = k.stride, Lw = k.L;
   const long long nwin = (long long)a.B * Lw;
@@ -280,6 +276,9 @@ __global__ void __launch_bounds__(128, WR == 32 ? 4 : 2) k_block_fwd_tc(const Bl
   }
   tc_fence_before();
   __syncthreads();
+#ifdef STG_TC_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][15] = clock64();
+#endif
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
 
@@ -301,7 +300,7 @@ static void launch_fwd(const BlkArgs& a, int total, int n0, size_t smem, cudaStr
 }  // namespace tc
 
 #ifdef STG_TC_TIMING
-extern "C" int stg_debug_tc_stamps(long long* out32) {
+extern "C" int stg_debug_tc_stamps_fwd(long long* out32) {
   return cudaMemcpyFromSymbol(out32, tc::g_tc_stamp, sizeof(long long) * 32) == cudaSuccess ? 0 : -1;
 }
 #endif

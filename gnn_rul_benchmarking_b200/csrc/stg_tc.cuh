@@ -408,5 +408,14 @@ inline int sm_count() {
   return n;
 }
 
+#ifdef STG_TC_TIMING
+// debug build only (-DSTG_TC_TIMING): clock64 stamps of CTA 0's second tile, threads 0 and 64
+static __device__ long long g_tc_stamp[2][16];          // per translation unit: [thread 0 | 64][stamp]
+#define STG_STAMP(n)                                                                              \
+  if (blockIdx.x == 0 && tile == cta + ncta && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][n] = clock64();
+#else
+#define STG_STAMP(n)
+#endif
+
 }  // namespace tc
 }  // namespace stg

@@ -19,13 +19,26 @@ for _ in range(3):
     alg.step(X, y)
 torch.cuda.synchronize()
 lib = _lib.load()
-buf = (C.c_longlong * 32)()
-assert lib.stg_debug_tc_stamps(buf) == 0
-for t in range(2):
-    st = [buf[t * 16 + i] for i in range(14)]
-    print("thread", 0 if t == 0 else 64, [st[i] - st[0] for i in range(14)])
-names = ["start", "x stored", "bar1", "issued FV", "FV done", "F/V stored", "bar2", "issued S", "S done", "softmax+st", "bar3",
-         "issued Z", "Z done", "end"]
-st = [buf[i] for i in range(14)]
-for i in range(1, 14):
-    print(f"  {names[i]:12s} +{st[i] - st[i - 1]:6d}  (thread 64: +{buf[16 + i] - buf[16 + i - 1]:6d})")
+buf = (C.c_longlong * 64)()
+half = (C.c_longlong * 32)()
+for kern, fn in enumerate((lib.stg_debug_tc_stamps_fwd, lib.stg_debug_tc_stamps_bwd)):
+    assert fn(half) == 0
+    for i in range(32):
+        buf[kern * 32 + i] = half[i]
+names = {0: ["start", "x stored", "bar1", "issued FV", "FV done", "F/V stored", "bar2", "issued S", "S done", "softmax+agg", "-", "-",
+             "-", "end"],
+         1: ["start", "loads+stores", "bar1", "issued dA", "dA done", "softmax bwd", "bar2", "issued dF/dV", "dF/dV done",
+             "dFV stored", "bar3", "issued dx/G", "dx/G done", "end"]}
+for kern in (0, 1):
+    print("forward" if kern == 0 else "backward", "tile, cycles (thread 0 | thread 64)")
+    base = kern * 32
+    prev = [buf[base], buf[base + 16]]
+    for i in range(1, 14):
+        cur = [buf[base + i], buf[base + 16 + i]]
+        if cur[0] <= 0:
+            continue
+        print(f"  {names[kern][i]:14s} +{cur[0] - prev[0]:6d} | +{cur[1] - prev[1]:6d}")
+        prev = cur
+    print(f"  total {prev[0] - buf[base]}")
+    print(f"  CTA 0: kernel start -> this (2nd) tile start {buf[base] - buf[base + 14]}, tile end -> kernel end {buf[base + 15] - buf[base + 13]}, "
+          f"whole CTA {buf[base + 15] - buf[base + 14]}")
