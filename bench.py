@@ -14,7 +14,11 @@ One JSON line on stdout (rank 0):
   e2e       same step through the reference-facing API (FC_STGNN.update) with pinned HOST buffers:
             H2D of X,y and D2H of the loss inside the timed region
   roofline  dominant kernel of libstgconv_b200.so, timed with CUDA events on its stream during a
-            second pass over the same steps (stg_profile_*), algorithmic bytes from DESIGN.md
+            second pass over the same steps (stg_profile_*), algorithmic bytes from DESIGN.md; block_kernels = HBM-side
+            and compute-side fraction of both graph-conv block kernels
+  extra     the same step on the north_star shape S2 (B=256) and on S1 at B=4096 (1 GPU only)
+  eager_cuda_baseline  the reference's eager ATen path on this GPU (oracle port with tensors on cuda:0)
+  dp_check  N>1: replicas bit-identical, fused NVLink exchange not timed out, fused == NCCL over 3 steps
   cpu_baseline  the CPU oracle port (oracle/fc_stgnn_oracle.py) on this box's host cores, bounded sample
 `--impl reference` times that CPU port alone (all host threads) and prints the same line shape.
 Timing: per-step CUDA-event pairs, L2 flushed (256 MiB memset) between steps outside the pairs,
@@ -65,6 +69,56 @@ def algorithmic_bytes(cfg, B):
 
 
 KERNEL_BYTES_KIND = {"k_block_fwd": "fwd", "k_block_bwd": "bwd"}
+
+
+def algorithmic_flops(cfg, B):
+    """FLOPs of the two blocks as the reference computes them: per graph 2MC^2 (mapping) + 2M^2C
+    (Gram) + 2M^2C (A.X) + 2MCH (theta) + ~8M^2 (softmax / mask); backward ~ 2x forward."""
+    T, N, h = cfg["num_patch"], cfg["num_node"], cfg["hidden_dim"]
+    C, H, M = 2 * h, h, 2 * N
+    per_graph = 2 * M * C * C + 4 * M * M * C + 2 * M * C * H + 8 * M * M
+    L = (T - 2) // 1 + 1 + (T - 2) // 2 + 1
+    fwd = per_graph * L * B
+    return {"fwd": fwd, "bwd": 2 * fwd}
+
+
+def measured_peak_tf32():
+    """Dense TF32 tensor peak.  MEASURED_PEAKS.json holds the measured dense bf16 figure; TF32 runs at half the
+    bf16 rate on this part (1.1 vs 2.25 PFLOP/s nominal), so the denominator is bf16_tflops / 2."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["bf16_tflops"]) / 2.0, "measured bf16 / 2"
+    except Exception:
+        return 1590.0 / 2.0, "fallback bf16 / 2"
+
+
+def ncu_metric(kernel, key):
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        with open(p) as fh:
+            return json.load(fh)["kernels"][kernel].get(key)
+    except Exception:
+        return None
+
+
+def kernel_rooflines(kern, cfg, B, peak):
+    """HBM-side and compute-side fraction of each graph-conv block kernel from its live CUDA-event time."""
+    ab, fl = algorithmic_bytes(cfg, B), algorithmic_flops(cfg, B)
+    tpeak, tsrc = measured_peak_tf32()
+    out = {}
+    for name, kind in KERNEL_BYTES_KIND.items():
+        if name not in kern:
+            continue
+        tot_ms, n = kern[name]
+        avg_s = tot_ms / n / 1e3
+        gbs = ab[kind] / avg_s / 1e9
+        tfs = fl[kind] / avg_s / 1e12
+        out[name] = {"avg_launch_us": round(avg_s * 1e6, 2), "algorithmic_bytes": ab[kind], "hbm_gbs": round(gbs, 1),
+                     "hbm_frac": gbs / peak, "algorithmic_flops": fl[kind], "tflops": round(tfs, 3),
+                     "tensor_frac": tfs / tpeak, "tensor_peak_tflops": tpeak, "tensor_peak_source": tsrc,
+                     "sm__pipe_tensor_pct_ncu": ncu_metric(name, "pipe_tensor_pct")}
+    return out
 
 
 def ncu_traffic(kernel):
@@ -213,6 +267,94 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def time_config(workload, B, dev, steps, warmup, flush):
+    """value / per-kernel times of one more (workload, batch) on a single GPU: the `extra` block of the line."""
+    from gnn_rul_benchmarking_b200 import _lib
+    from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
+    cfg = model_cfg(workload)
+    torch.manual_seed(0)
+    alg = get_algorithm_class("FC_STGNN")(cfg, HPARAMS, dev).to(dev)
+    alg.train()
+    alg.enable_cuda_graph(B)
+    g = torch.Generator().manual_seed(99)
+    X = torch.rand(B, cfg["num_node"], cfg["num_patch"] * cfg["patch_size"], generator=g).to(dev)
+    y = torch.rand(B, 1, generator=g).to(dev)
+    for _ in range(warmup):
+        alg.step(X, y)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record()
+        alg.step(X, y)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    alg.disable_cuda_graph()
+    with _lib.kernel_profile() as prof:
+        for _ in range(steps):
+            flush.zero_()
+            alg.step(X, y)
+        torch.cuda.synchronize()
+    kern = prof.result()
+    peak, _ = measured_peak_gbs()
+    return {"workload": f"{workload}: {WORKLOADS[workload][1]}", "batch": B, "value": B / (ms / 1e3), "unit": UNIT,
+            "ms_per_step": ms, "steps": steps, "kernels_us": {k: round(1e3 * t / n, 2) for k, (t, n) in kern.items()},
+            "block_kernels": kernel_rooflines(kern, cfg, B, peak)}
+
+
+def eager_cuda_baseline(cfg, B, dev, steps=10, warmup=3):
+    """The reference's own eager-ATen path on this GPU (main.py:34 defaults to cuda:0): the oracle port's update with
+    every tensor on the device -- cuBLAS bmm, cuDNN conv / BatchNorm, ~500 launches per step."""
+    from oracle import fc_stgnn_oracle as orc
+    torch.manual_seed(0)
+    alg = orc.OracleAlgorithm(cfg, HPARAMS, seed=0, device=dev)
+    X = torch.rand(B, cfg["num_node"], cfg["num_patch"] * cfg["patch_size"], device=dev)
+    y = torch.rand(B, 1, device=dev)
+    for _ in range(warmup):
+        alg.update(X, y)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        alg.update(X, y)            # .item() on the loss synchronises every step, as the reference does
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / steps
+    return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "what": "oracle port of algorithms.py:67-76 with all tensors on cuda:0 (eager ATen: cuBLAS / cuDNN), wall clock"}
+
+
+def dp_check(alg, dev, world, rank, cfg, B):
+    """Correctness evidence for the multi-GPU line: replicas bit-identical after the timed loop, the fused NVLink
+    exchange never timed out, and 3 steps of the fused exchange equal 3 steps of NCCL all-reduce + Adam."""
+    import torch.distributed as dist
+    from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
+    flat = alg.model.engine.flat["param"]
+    mine = flat.double().sum().reshape(1)
+    mine2 = (flat.double() * torch.arange(1, flat.numel() + 1, device=dev, dtype=torch.float64)).sum().reshape(1)
+    both = torch.cat([mine, mine2])
+    gathered = [torch.zeros_like(both) for _ in range(world)]
+    dist.all_gather(gathered, both)
+    identical = all(torch.equal(gathered[0], t) for t in gathered)
+    timed_out = bool(alg.p2p_timed_out()) if getattr(alg, "_dp_p2p", False) else False
+    # fused exchange vs NCCL on fresh replicas and identical data
+    res = []
+    for p2p in ("auto", False):
+        torch.manual_seed(7)
+        a2 = get_algorithm_class("FC_STGNN")(cfg, HPARAMS, dev).to(dev)
+        a2.model.positional_encoding.dropout.p = 0.0
+        a2.train()
+        a2.attach_data_parallel(p2p=p2p)
+        g = torch.Generator().manual_seed(4321 + rank)
+        for it in range(3):
+            X = torch.rand(B, cfg["num_node"], cfg["num_patch"] * cfg["patch_size"], generator=g).to(dev)
+            y = torch.rand(B, 1, generator=g).to(dev)
+            a2.update(X, y, it)
+        res.append((a2.model.engine.flat["param"].clone(), bool(getattr(a2, "_dp_p2p", False))))
+    dmax = float((res[0][0] - res[1][0]).abs().max())
+    return {"replicas_bit_identical": bool(identical), "p2p_timed_out": timed_out,
+            "fused_vs_nccl_max_abs_dparam_3_steps": dmax, "fused_exchange_used": res[0][1]}
+
+
 def run_native(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -290,6 +432,9 @@ def run_native(args):
     with _lib.kernel_profile() as prof:
         timed(step_resident, args.steps)
     kern = prof.result()
+    dpc = dp_check(alg, dev, world, rank, cfg, B) if world > 1 else None
+    if world > 1 and (dpc["p2p_timed_out"] or not dpc["replicas_bit_identical"]):
+        raise SystemExit(f"bench.py: data-parallel replicas diverged / exchange timed out: {dpc}")
 
     if rank != 0:
         if world > 1:
@@ -312,12 +457,20 @@ def run_native(args):
                 "algorithmic_bytes": nbytes,
                 "avg_launch_us": avg_s * 1e6,
                 "share_of_lib_time": tot_ms / max(1e-9, sum(t for t, _ in kern.values())),
-                "kernels_us": {k: round(1e3 * t / n2, 2) for k, (t, n2) in kern.items()}}
+                "kernels_us": {k: round(1e3 * t / n2, 2) for k, (t, n2) in kern.items()},
+                "block_kernels": kernel_rooflines(kern, cfg, B, peak)}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ms_cpu, done, threads = cpu_reference_steps(cfg, B, 10_000, 2, budget_s=args.cpu_budget)
         cpu = {"value": B / (ms_cpu / 1e3), "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{done} update steps of B={B} ({args.workload}), {ms_cpu:.1f} ms/step, oracle port"}
+    extra, eager = None, None
+    if world == 1 and not args.no_extra:
+        extra = []
+        for wl, bb in (("S2", 256), ("S1", 4096)):
+            if (wl, bb) != (args.workload, B):
+                extra.append(time_config(wl, bb, dev, max(5, min(args.steps, 20)), 5, flush))
+        eager = eager_cuda_baseline(cfg, B, dev)
     h2d = Xh[0].numel() * 4 + yh[0].numel() * 4
     line = {
         "metric": METRIC, "value": world * B / (ms_res / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -332,6 +485,7 @@ def run_native(args):
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(round(launches / args.steps)) * args.steps,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
+        "extra": extra, "eager_cuda_baseline": eager, "dp_check": dpc,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -348,6 +502,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="windows per GPU per step")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra S2 / B=4096 / eager-CUDA measurements")
     ap.add_argument("--nccl", action="store_true", help="N>1: NCCL all-reduce + Adam instead of the fused NVLink kernel")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

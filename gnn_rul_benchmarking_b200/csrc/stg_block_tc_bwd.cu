@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl.tmem_base)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  tc_prologue(a, k, sm, L, SPLIT);
+  tc_prologue(a, k, sm, L, SPLIT, true);
   float* cst = reinterpret_cast<float*>(sm + L.cst);
   // BN1 backward coefficients: [0]=a1 [1]=c1 [2]=mu1 [3]=r1 [4]=g1*r1 [5]=q1 [6]=q2
   if (tid < 8) {
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
     for (int q = 0; q < 7; ++q) cst[kCstBn1 + q * 8 + tid] = v[q];
   }
   // operand buffers whose pad parts are read by the tensor core but never written per tile
-  for (int idx = tid; idx < (L.wcb - L.ra) / 16; idx += 128) reinterpret_cast<float4*>(sm + L.ra)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int idx = tid; idx < (L.wc2 - L.ra) / 16; idx += 128) reinterpret_cast<float4*>(sm + L.ra)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   float* red = cst + kCstRed;         // G[24][17] (column 16 = column sums of [dF | dV]) then dbt[8]
   for (int idx = tid; idx < 24 * 17 + 8; idx += 128) red[idx] = 0.f;
   fence_async_smem();
@@ -66,21 +66,19 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   const uint32_t tmem = ctl.tmem_base;
   const uint32_t lane_t = tmem + ((uint32_t)(warp * 32) << 16);
   constexpr uint32_t regA = 0, regB = 128;
-  const uint32_t xk_lo = dlo(smem_u32(sm + L.xk), 2048), xkl_lo = dlo(smem_u32(sm + L.xkl), 2048),
-                 wcb_lo = dlo(smem_u32(sm + L.wcb), 512), wcbl_lo = dlo(smem_u32(sm + L.wcbl), 512),
+  const uint32_t t2l_lo = dlo(smem_u32(sm + L.t2) + 16 * 1024, 2048),
                  yk_lo = dlo(smem_u32(sm + L.yk), 2048), ra_lo = dlo(smem_u32(sm + L.ra), 512),
                  rb_lo = dlo(smem_u32(sm + L.rb), 512), t1_lo = dlo(smem_u32(sm + L.t1), WR * 128),
                  t2_lo = dlo(smem_u32(sm + L.t2), WR * 128), t1g_lo = dlo(smem_u32(sm + L.t1), 512),
                  t2k_lo = dlo(smem_u32(sm + L.t2), 2048), wc2_lo = dlo(smem_u32(sm + L.wc2), 256),
                  wc2l_lo = dlo(smem_u32(sm + L.wc2l), 256);
-  float4* xk4 = reinterpret_cast<float4*>(sm + L.xk);
-  float4* xkl4 = reinterpret_cast<float4*>(sm + L.xkl);
   float4* yk4 = reinterpret_cast<float4*>(sm + L.yk);
   unsigned char* ra = sm + L.ra;
   unsigned char* rb = sm + L.rb;
   unsigned char* t1 = sm + L.t1;
   unsigned char* t2 = sm + L.t2;
-  float4* t2k4 = reinterpret_cast<float4*>(t2);       // [dF | dV] rows, K-major, for the dx projection
+  float4* t2k4 = reinterpret_cast<float4*>(t2);       // [dF | dV] rows, K-major, for the dx projection ...
+  float4* t2l4 = reinterpret_cast<float4*>(t2 + 16 * 1024);      // ... and their tf32 residuals
 
   const int wl = tid / WR, i = tid - wl * WR;
   const bool row_ok = i < M;
@@ -268,7 +266,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
       for (int c = 0; c < kCP; ++c) sof[c] += fv[c];
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
-        st_hl<SPLIT>(&t2k4[q * 128 + tid], &xk4[q * 128 + tid], fv[4 * q], fv[4 * q + 1], fv[4 * q + 2], fv[4 * q + 3]);
+        st_hl<SPLIT>(&t2k4[q * 128 + tid], &t2l4[q * 128 + tid], fv[4 * q], fv[4 * q + 1], fv[4 * q + 2], fv[4 * q + 3]);
         *rec_ptr(t1, tid, q) = t2k4[q * 128 + tid];
       }
     }
@@ -286,7 +284,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
         mma_ss(tmem + regA, dsc(t2k_lo + ks * 256, kHiK), dsc(wc2_lo + ks * 32, kHiK), id_x, ks);
         if (SPLIT) {
           mma_ss(tmem + regA, dsc(t2k_lo + ks * 256, kHiK), dsc(wc2l_lo + ks * 32, kHiK), id_x, 1);
-          mma_ss(tmem + regA, dsc(xk_lo + ks * 256, kHiK), dsc(wc2_lo + ks * 32, kHiK), id_x, 1);
+          mma_ss(tmem + regA, dsc(t2l_lo + ks * 256, kHiK), dsc(wc2_lo + ks * 32, kHiK), id_x, 1);
         }
       }
 #pragma unroll
@@ -404,7 +402,7 @@ int launch_block_backward_tc(const BlkArgs& a, const BlkPlan& p, cudaStream_t s)
   using namespace tc;
   const SmemLayout L = make_layout(p.tc_wr, true, p.tc_split != 0);
   int n0 = 0, total = 0;
-  const int per_sm = (size_t)L.total * 2 <= 220 * 1024 ? 2 : 1;
+  const int per_sm = 2 * ((size_t)L.total + 1024) <= 227 * 1024 ? 2 : 1;      // 227 KB usable per SM, 1 KB reserved per CTA
   split_ctas(a, p.tc_wr, per_sm * sm_count(), &n0, &total);
   ProfScope ps(kProfBwdMain, s);
 #define STG_TC_BWD(WR, NT)                                                  \

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(128, WR == 32 ? 4 : 2) k_block_fwd_tc(const Bl
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl.tmem_base)), "r"(128));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  tc_prologue(a, k, sm, L, SPLIT);
+  tc_prologue(a, k, sm, L, SPLIT, false);
   float* cst = reinterpret_cast<float*>(sm + L.cst);
   if (!TRAIN && tid < 8) {
     float a1 = 0.f, c1 = 0.f;

@@ -160,18 +160,20 @@ constexpr int kCstFloats = 176 + 24 * 17 + 32;
 __host__ __device__ inline SmemLayout make_layout(int WR, bool bwd, bool split) {
   SmemLayout l;
   int o = 0;
-  l.xk = o; o += 4 * 128 * 16;
-  l.xkl = o; if (split) o += 4 * 128 * 16;
+  // forward: x / F rows (K-major, + residuals), V rows, projection weights.  backward: row records, dY' | V rows,
+  // the two transposed operands (t2 doubles as the K-major [dF | dV] rows + residuals afterwards), dx weights.
+  l.xk = o; if (!bwd) o += 4 * 128 * 16;
+  l.xkl = o; if (!bwd && split) o += 4 * 128 * 16;
   l.vs = o; if (!bwd) o += 128 * 32;
   l.ra = o; if (bwd) o += 128 * 128;
   l.rb = o; if (bwd) o += 128 * 128;
   l.yk = o; if (bwd) o += 2 * 2 * 128 * 16;
   l.t1 = o; if (bwd) o += 4 * WR * 128;
-  l.t2 = o; if (bwd) o += 4 * WR * 128;
-  l.wcb = o; o += 4 * 32 * 16;
-  l.wcbl = o; if (split) o += 4 * 32 * 16;
-  l.wc2 = o; o += 6 * 16 * 16;
-  l.wc2l = o; if (split) o += 6 * 16 * 16;
+  l.t2 = o; if (bwd) o += (4 * WR * 128 > 28 * 1024 ? 4 * WR * 128 : 28 * 1024);
+  l.wcb = o; if (!bwd) o += 4 * 32 * 16;
+  l.wcbl = o; if (!bwd && split) o += 4 * 32 * 16;
+  l.wc2 = o; if (bwd) o += 6 * 16 * 16;
+  l.wc2l = o; if (bwd && split) o += 6 * 16 * 16;
   o = (o + 1023) / 1024 * 1024;
   l.cst = o; o += kCstFloats * 4;
   l.total = o + 1024;      // slack for the manual 1024-byte alignment of the dynamic window
@@ -197,7 +199,8 @@ struct TcCtl {
 
 // Prologue shared by forward and backward: projection weights, biases, BN0 coefficients.
 // Training: copied from the coefficient table written by k_block_prep / k_xmoments_prep; eval: from running stats.
-STG_DEVINL void tc_prologue(const BlkArgs& a, const BlkDev& k, unsigned char* sm, const SmemLayout& L, bool split) {
+STG_DEVINL void tc_prologue(const BlkArgs& a, const BlkDev& k, unsigned char* sm, const SmemLayout& L, bool split,
+                            bool bwd) {
   float* cst = reinterpret_cast<float*>(sm + L.cst);
   float* wcb = reinterpret_cast<float*>(sm + L.wcb);
   float* wcbl = reinterpret_cast<float*>(sm + L.wcbl);
@@ -218,9 +221,10 @@ STG_DEVINL void tc_prologue(const BlkArgs& a, const BlkDev& k, unsigned char* sm
       const int o = idx >> 4, c = idx & 15;
       const float v = o < kCPH ? WcT[c * kCPH + o] : 0.f;
       const float vh = rtf(v);
-      wcb[((c >> 2) * 32 + o) * 4 + (c & 3)] = vh;
-      if (split) wcbl[((c >> 2) * 32 + o) * 4 + (c & 3)] = rtf(v - vh);
-      if (o < kCPH) {
+      if (!bwd) {
+        wcb[((c >> 2) * 32 + o) * 4 + (c & 3)] = vh;
+        if (split) wcbl[((c >> 2) * 32 + o) * 4 + (c & 3)] = rtf(v - vh);
+      } else if (o < kCPH) {
         wc2[((o >> 2) * 16 + c) * 4 + (o & 3)] = vh;
         if (split) wc2l[((o >> 2) * 16 + c) * 4 + (o & 3)] = rtf(v - vh);
       }
@@ -246,9 +250,10 @@ STG_DEVINL void tc_prologue(const BlkArgs& a, const BlkDev& k, unsigned char* sm
         else if (o >= kCP && o - kCP < H) v = k.Wt[(o - kCP) * C + c] * cst[kCstA0 + c];
       }
       const float vh = rtf(v);
-      wcb[((c >> 2) * 32 + o) * 4 + (c & 3)] = vh;
-      if (split) wcbl[((c >> 2) * 32 + o) * 4 + (c & 3)] = rtf(v - vh);
-      if (o < kCPH) {
+      if (!bwd) {
+        wcb[((c >> 2) * 32 + o) * 4 + (c & 3)] = vh;
+        if (split) wcbl[((c >> 2) * 32 + o) * 4 + (c & 3)] = rtf(v - vh);
+      } else if (o < kCPH) {
         wc2[((o >> 2) * 16 + c) * 4 + (o & 3)] = vh;
         if (split) wc2l[((o >> 2) * 16 + c) * 4 + (o & 3)] = rtf(v - vh);
       }

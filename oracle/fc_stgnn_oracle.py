@@ -50,10 +50,10 @@ def num_windows(T: int, w: int, s: int) -> int:
     return (T - w) // s + 1
 
 
-def decay_mask(N: int, w: int, decay: float, dtype=torch.float32) -> torch.Tensor:
+def decay_mask(N: int, w: int, decay: float, dtype=torch.float32, device=None) -> torch.Tensor:
     """mask[i,k] = decay^|i//N - k//N|  (closed form of Mask_Matrix, Model_Base.py:150-170)."""
     t = torch.arange(w * N) // N
-    return torch.as_tensor(decay, dtype=torch.float64).pow((t[:, None] - t[None, :]).abs().double()).to(dtype)
+    return torch.as_tensor(decay, dtype=torch.float64).pow((t[:, None] - t[None, :]).abs().double()).to(dtype).to(device)
 
 
 def windows(x: torch.Tensor, w: int, s: int) -> torch.Tensor:
@@ -61,7 +61,7 @@ def windows(x: torch.Tensor, w: int, s: int) -> torch.Tensor:
     Same elements as Conv_GraphST + the transpose/reshape at Model_Base.py:194-198."""
     B, T, N, C = x.shape
     L = num_windows(T, w, s)
-    idx = (torch.arange(L)[:, None] * s + torch.arange(w)[None, :])       # [L,w]
+    idx = (torch.arange(L, device=x.device)[:, None] * s + torch.arange(w, device=x.device)[None, :])       # [L,w]
     return x[:, idx].reshape(B, L, w * N, C)
 
 
@@ -103,10 +103,10 @@ def block_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, str
     # --- adjacency (Model_Base.py:49-63): learned map, Gram, diag out, lrelu, softmax, +I
     Fm = G @ Wm.t() + bm
     S = Fm @ Fm.transpose(-1, -2)                              # [B,L,M,M]
-    eye = torch.eye(M, dtype=x.dtype)
+    eye = torch.eye(M, dtype=x.dtype, device=x.device)
     Lam = F.leaky_relu(S - 1e8 * eye, LEAKY)
     P = torch.softmax(Lam, dim=-1)
-    A = (P + eye) * decay_mask(N, w, decay, x.dtype)           # Model_Base.py:203
+    A = (P + eye) * decay_mask(N, w, decay, x.dtype, x.device)           # Model_Base.py:203
     # --- BN over the unfolded rows (Model_Base.py:206-208)
     k0 = prefix + "BN."
     if training:
@@ -332,9 +332,14 @@ class OracleAlgorithm:
     """algorithms/algorithms.py:51-76 (class FC_STGNN): Adam(lr, weight_decay) + MSE;
     update(X, y) = forward -> mse -> zero_grad -> backward -> step -> {'loss': float}."""
 
-    def __init__(self, cfg: dict, hparams: dict, sd: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0):
+    def __init__(self, cfg: dict, hparams: dict, sd: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0,
+                 device=None):
+        """device: None / cpu = the reference's CPU path; "cuda:0" = the same eager ATen ops on the GPU (the
+        reference's default device, main.py:34) -- bench.py's eager_cuda_baseline."""
         self.cfg = dict(cfg)
         self.sd = sd if sd is not None else init_state(cfg, seed)
+        if device is not None:
+            self.sd = {k: v.detach().to(device) for k, v in self.sd.items()}
         self.params = [v.requires_grad_(True) for k, v in self.sd.items() if is_param(k)]
         self.optimizer = torch.optim.Adam(self.params, lr=hparams["learning_rate"],
                                           weight_decay=hparams["weight_decay"])
