@@ -111,7 +111,8 @@ class FC_STGNN(Algorithm):
         N, L = m.MPNN1.num_sensors, m.num_patch * m.patch_size
         self._gX = torch.zeros(batch_size, N, L, device=dev)
         self._gy = torch.zeros(batch_size, 1, device=dev)
-        eng.graph_seed = (int(torch.randint(0, 2 ** 62, (1,)).item()), torch.zeros(1, dtype=torch.int64, device=dev))
+        from .engine import draw_cuda_seed
+        eng.graph_seed = (draw_cuda_seed(dev), torch.zeros(1, dtype=torch.int64, device=dev))
         snap = [t.clone() for t in (fl["param"], st["exp_avg"], st["exp_avg_sq"], st["step"])]
         bufs = [b for b in m.buffers()]
         snap_b = [b.clone() for b in bufs]

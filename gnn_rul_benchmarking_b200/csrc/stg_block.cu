@@ -244,6 +244,48 @@ __global__ void __launch_bounds__(256) k_xmoments_prep(const BlkArgs a, int CP, 
   }
 }
 
+// Same job for C == 16 (every reference hyper-parameter set with hidden_dim 8), without shared-memory atomics:
+// one warp walks the [N,16] slabs of ONE time step over a slice of the batch; lane l always meets feature l % 16
+// (the slab is read as consecutive floats and 32 % 16 == 0), so the moments stay in two registers per lane, lanes l and
+// l + 16 are folded with one shuffle and every warp issues 32 double atomics in all.  grid (ceil(T * wpt / 8)), 256.
+__global__ void __launch_bounds__(256) k_xmoments_prep16(const BlkArgs a, int CP, int HP, double* xmom,
+                                                         unsigned* counter, int wpt) {
+  __shared__ double ssum[48], ssq[48];
+  __shared__ float sa0[48], sc0[48], sWt[24 * 48];
+  __shared__ int s_last;
+  const int B = a.B, T = a.T, N = a.N;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw < T * wpt) {
+    const int t = gw % T, sl = gw / T;
+    const int NC = N * 16;
+    float s1 = 0.f, s2 = 0.f;
+    for (int b = sl; b < B; b += wpt) {
+      const float* p = a.x + ((size_t)b * T + t) * NC;
+      for (int e = lane; e < NC; e += 32) {
+        const float v = __ldg(p + e);
+        s1 += v;
+        s2 = fmaf(v, v, s2);
+      }
+    }
+    s1 += __shfl_down_sync(0xffffffffu, s1, 16);
+    s2 += __shfl_down_sync(0xffffffffu, s2, 16);
+    if (lane < 16) {
+      atomicAdd(&xmom[t * 16 + lane], (double)s1);
+      atomicAdd(&xmom[(size_t)T * 16 + t * 16 + lane], (double)s2);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int z = 0; z < a.nblk; ++z) {
+    block_prep_body(a, z, CP, HP, xmom, ssum, ssq, sa0, sc0, sWt);
+    __syncthreads();
+  }
+}
+
 // BN0 statistics (batch or running), folded projection [Wm | Wtheta.diag(g0 r0)]^T and biases.
 template <int CP, int HP, bool TRAIN>
 STG_DEVINL void block_prologue(const BlkArgs& a, const BlkDev& k, Carve<CP, HP>& sm) {
@@ -1202,6 +1244,15 @@ int launch_xmoments_prep(const BlkArgs& a, const BlkPlan& p, double* xmom, unsig
   int nb = (a.B + 15) / 16;
   if (nb > 64) nb = 64;
   ProfScope ps(kProfXmoments, s);
+  if (a.C == 16 && !getenv("STG_XMOM_GENERIC")) {
+    // warps per time step: enough warps for ~8 per SM, at most one per sample
+    int wpt = (148 * 8 + a.T - 1) / a.T;
+    if (wpt > a.B) wpt = a.B;
+    if (wpt < 1) wpt = 1;
+    const int warps = a.T * wpt;
+    k_xmoments_prep16<<<(warps + 7) / 8, 256, 0, s>>>(a, p.CP, p.HP, xmom, counter, wpt);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+  }
   k_xmoments_prep<<<dim3(a.T, nb), 256, 0, s>>>(a, p.CP, p.HP, xmom, counter);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -1,9 +1,11 @@
 """Data-parallel plumbing for the unchanged caller.
 
 `Algorithm.update` runs zero_grad -> backward -> step back to back (algorithms/algorithms.py:72-74)
-with no hook point, so the gradient exchange fires from inside backward: a post-accumulate-grad
-hook per parameter counts arrivals and, on the last one, all-reduces ONE flat fp32 buffer
-(FC_STGNN FD004: 66 429 floats = 266 KB) and scatters the mean back into the .grad tensors.
+with no hook point, so the gradient exchange fires from inside backward: the first post-accumulate-grad
+hook of a backward pass queues an end-of-backward callback on the autograd engine, which all-reduces ONE
+flat fp32 buffer (FC_STGNN FD004: 66 429 floats = 266 KB) and scatters the mean back into the .grad
+tensors.  Parameters that took no part in the pass (the reference keeps never-used TemporalConvNet.net0/net1
+modules, models/ST_GCN/Model.py:110-132) contribute zeros and keep grad = None, exactly as without the hook.
 BatchNorm statistics stay per rank (PyTorch-DDP default); parameters and buffers are broadcast
 from rank 0 once at attach time.  Works with any torch.distributed backend (nccl on the GPUs,
 gloo in the CPU tests).
@@ -44,23 +46,28 @@ class FlatGradAllReduce:
         self.n_allreduce = 0
 
     def _hook(self, _p):
-        self._pending += 1
-        if self._pending < len(self.params):
-            return
+        # first gradient of this backward pass: run the exchange once the whole pass is done (every parameter that
+        # is going to get a gradient has it by then; unused parameters never fire a hook and must not be waited for)
+        if not self._pending:
+            self._pending = 1
+            torch.autograd.Variable._execution_engine.queue_callback(self._exchange)
+
+    def _exchange(self):
         self._pending = 0
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        used = [p.grad is not None for p in self.params]
+        grads = [p.grad if u else torch.zeros_like(p) for p, u in zip(self.params, used)]
         flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         flat.div_(self.world)
         off = 0
-        views = []
-        for g in grads:
-            views.append(flat[off:off + g.numel()].view_as(g))
+        dst, views = [], []
+        for g, u in zip(grads, used):
+            if u:                                   # same set on every rank: the model and its inputs' shapes agree
+                dst.append(g)
+                views.append(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
-        torch._foreach_copy_(grads, views)
-        for p, g in zip(self.params, grads):
-            if p.grad is None:
-                p.grad = g
+        if dst:
+            torch._foreach_copy_(dst, views)
         self.n_allreduce += 1
 
     def detach(self):

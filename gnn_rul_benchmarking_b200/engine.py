@@ -150,7 +150,10 @@ class ModelEngine:
             dr.seed = self.graph_seed[0]                               # + device counter, ticked per step
             dr.step_dev = self.graph_seed[1].data_ptr()
         elif d.pe_dropout > 0:
-            dr.seed = int(torch.randint(0, 2 ** 62, (1,)).item())     # CPU generator: follows torch.manual_seed
+            # like the reference's nn.Dropout on cuda, consume the CUDA generator (seed + Philox offset, advanced on the
+            # host without launching anything): follows torch.manual_seed, leaves the CPU stream -- and with it the
+            # DataLoader / DeviceLoader permutations -- exactly where the reference run would have it
+            dr.seed = draw_cuda_seed(X.device)
         return dr, keep
 
     # ---------------------------------------------------------------- forward / backward
@@ -305,6 +308,15 @@ def model_forward(engine: ModelEngine, X: torch.Tensor) -> torch.Tensor:
     return pred
 
 
+def draw_cuda_seed(device) -> int:
+    """A 62-bit seed from the device's default CUDA generator: (seed, Philox offset), offset advanced on the host."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[idx]
+    off = int(gen.get_offset())
+    gen.set_offset(off + 4)
+    return (int(gen.initial_seed()) * 0x9E3779B97F4A7C15 + off * 0xD1B54A32D192ED03 + 1) % (2 ** 62)
+
+
 class StgAdam(torch.optim.Optimizer):
     """torch.optim.Adam(lr, betas, eps, weight_decay) semantics (algorithms.py:60-64) as ONE kernel
     over the engine's flat parameter / gradient buffers (stg_adam_step)."""
@@ -342,6 +354,37 @@ class StgAdam(torch.optim.Optimizer):
                 self.state[p] = dict(step=st["step"], exp_avg=st["exp_avg"][off:off + p.numel()].view_as(p),
                                      exp_avg_sq=st["exp_avg_sq"][off:off + p.numel()].view_as(p))
         return fl, st
+
+    def state_dict(self):
+        """Standard torch.optim layout; the per-parameter exp_avg / exp_avg_sq entries are views of the flat moment
+        buffers the kernel updates, `step` is the shared device counter."""
+        self._state()
+        return super().state_dict()
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        """Copies the loaded moments and step INTO the flat buffers (torch's implementation would rebind
+        self.state[p] to fresh tensors the kernel never reads)."""
+        fl, st = self._state()
+        groups = state_dict["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        params = [t for _, t in param_tensors(self.engine.model)]
+        if len(ids) != len(params):
+            raise ValueError("loaded optimizer state has a different number of parameters")
+        step = None
+        for pid, p, off in zip(ids, params, fl["offsets"]):
+            ent = state_dict["state"].get(pid)
+            if ent is None:
+                continue
+            st["exp_avg"][off:off + p.numel()].copy_(ent["exp_avg"].reshape(-1))
+            st["exp_avg_sq"][off:off + p.numel()].copy_(ent["exp_avg_sq"].reshape(-1))
+            step = ent["step"] if step is None else step
+        if step is not None:
+            st["step"].fill_(int(step))
+        for g, new in zip(self.param_groups, groups):
+            for k, v in new.items():
+                if k != "params":
+                    g[k] = v
 
     def zero_grad(self, set_to_none: bool = False):
         fl = self.engine.flatten()

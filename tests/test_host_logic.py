@@ -65,6 +65,10 @@ def _dp_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(100 + rank)                                  # different init per rank: broadcast must fix it
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.BatchNorm1d(5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    # a registered module that forward never uses (the reference's TemporalConvNet keeps net0 / net1 like this,
+    # models/ST_GCN/Model.py:110-132): its parameters get no gradient and must not stall or corrupt the exchange
+    net.add_module("dead", torch.nn.Linear(3, 3))
+    net.forward = lambda x: net[3](net[2](net[1](net[0](x))))
     hook = FlatGradAllReduce(net)
     opt = torch.optim.Adam(net.parameters(), lr=1e-2, weight_decay=1e-4)
     g = torch.Generator().manual_seed(7)
@@ -75,6 +79,7 @@ def _dp_worker(rank, world, port, q):
         opt.zero_grad()
         loss.backward()
         opt.step()
+    assert net.dead.weight.grad is None
     flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)

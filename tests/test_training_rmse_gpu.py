@@ -67,3 +67,45 @@ def test_rmse_after_equal_epochs(use_graph):
     print(f"RMSE new {rmse_new:.4f}  ref {rmse_ref:.4f}  (untrained predictor ~{orc.rmse(torch.full_like(pref, 0.5), yte.view(-1), MAX_RUL):.1f})")
     assert abs(rmse_new - rmse_ref) <= 0.05
     assert float((pred - pref).abs().max()) * MAX_RUL < 0.05       # every prediction, not only their RMSE
+
+
+def test_rmse_statistics_with_the_engines_own_dropout_under_cuda_graph():
+    """The +-0.05 test above pins the dropout masks.  Here both sides draw their own (the reference from torch's
+    generator, the engine from its counter-based generator inside the replayed CUDA graph), so single runs differ;
+    over 5 seeds x 5000 windows the MEAN test RMSE of the engine must sit inside the oracle's own seed-to-seed
+    spread, and its spread must be of the same size."""
+    from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
+    from gnn_rul_benchmarking_b200.configs import CONFIGS, TRAIN_PARAMS
+    dev = torch.device("cuda:0")
+    cfg = CONFIGS["FD004"]
+    bs, epochs, ntrain, ntest = 100, 2, 5000, 500
+    new, ref = [], []
+    for seed in range(5):
+        gen = torch.Generator().manual_seed(7000 + seed)
+        Xtr, ytr = _synthetic(ntrain, gen)
+        Xte, yte = _synthetic(ntest, gen)
+        torch.manual_seed(seed)                                # fix_randomness(run_id), utils.py:63-69
+        alg = get_algorithm_class("FC_STGNN")(cfg, TRAIN_PARAMS, dev)
+        sd = {k: v.detach().clone() for k, v in alg.model.state_dict().items()}
+        oracle = orc.OracleAlgorithm(cfg, TRAIN_PARAMS, sd={k: v.clone() for k, v in sd.items()})
+        alg = alg.to(dev)
+        alg.train()
+        alg.enable_cuda_graph(bs)
+        Xd, yd = Xtr.to(dev), ytr.to(dev)
+        torch.manual_seed(100 + seed)                          # the oracle's dropout stream
+        for ep in range(epochs):
+            perm = torch.randperm(ntrain, generator=gen)
+            for i in range(0, ntrain, bs):
+                idx = perm[i:i + bs]
+                alg.step(Xd[idx.to(dev)], yd[idx.to(dev)])
+                oracle.update(Xtr[idx], ytr[idx])              # dropout_keep=None: F.dropout draws its own mask
+        alg.eval()
+        with torch.no_grad():
+            pred = alg.model(Xte.to(dev)).cpu().view(-1)
+        new.append(orc.rmse(pred, yte.view(-1), MAX_RUL))
+        ref.append(orc.rmse(oracle.predict(Xte).view(-1), yte.view(-1), MAX_RUL))
+    new, ref = torch.tensor(new), torch.tensor(ref)
+    print(f"test RMSE over 5 seeds: engine {new.tolist()}  oracle {ref.tolist()}")
+    spread = float(ref.max() - ref.min())
+    assert abs(float(new.mean() - ref.mean())) <= max(spread, 0.05), (new.tolist(), ref.tolist())
+    assert float(new.max() - new.min()) <= 3.0 * max(spread, 0.05)
