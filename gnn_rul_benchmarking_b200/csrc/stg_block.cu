@@ -125,19 +125,21 @@ static size_t carve_bytes(int CP, int HP, int rows_max, int C, int wpc, int slot
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline int coef_floats(int CP, int HP, int T) { return 4 * CP + (CP + HP) + 4 + CP * (CP + HP) + T; }
 
+// `tid` of `nt` threads work on block z (the callers give every block its own slice of the CTA and its own scratch,
+// so that the tables of both blocks are built side by side); all threads of the CTA must call it (CTA barriers).
 STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const double* xmom, double* ssum,
-                                double* ssq, float* sa0, float* sc0, float* sWt) {
+                                double* ssq, float* sa0, float* sc0, float* sWt, int tid, int nt) {
   const BlkDev& k = a.b[z];
-  const int C = a.C, T = a.T, H = k.H, tid = threadIdx.x, CPH = CP + HP;
+  const int C = a.C, T = a.T, H = k.H, CPH = CP + HP;
   float* tab = k.coef;
   float* mu0 = tab; float* r0 = mu0 + CP; float* a0 = r0 + CP; float* c0 = a0 + CP;
   float* biasc = c0 + CP; float* pw = biasc + CPH; float* WcT = pw + 4; float* cnt = WcT + CP * CPH;
   if (tid < 48) { ssum[tid] = 0.0; ssq[tid] = 0.0; }
-  for (int i = tid; i < H * C; i += 256) sWt[i] = k.Wt[i];      // staged: the bias loop below walks rows of it
+  for (int i = tid; i < H * C; i += nt) sWt[i] = k.Wt[i];      // staged: the bias loop below walks rows of it
   __syncthreads();
   // weighted moments of x over time: thread (c, slice of t)
   {
-    const int c = tid % CP, sl = tid / CP, nsl = 256 / CP;
+    const int c = tid % CP, sl = tid / CP, nsl = nt / CP;
     if (c < C && sl < nsl) {
       double s = 0.0, q = 0.0;
       for (int t = sl; t < T; t += nsl) {
@@ -151,7 +153,7 @@ STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const d
       atomicAdd(&ssq[c], q);
     }
   }
-  for (int t = tid; t < T; t += 256) cnt[t] = (float)cover_count(t, k.w, k.stride, k.L);
+  for (int t = tid; t < T; t += nt) cnt[t] = (float)cover_count(t, k.w, k.stride, k.L);
   if (tid < 4) pw[tid] = powf(k.decay, (float)tid);
   __syncthreads();
   if (tid < CP) {
@@ -174,7 +176,7 @@ STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const d
     sa0[c] = av; sc0[c] = cv;
   }
   __syncthreads();
-  for (int idx = tid; idx < CP * CPH; idx += 256) {
+  for (int idx = tid; idx < CP * CPH; idx += nt) {
     const int c = idx / CPH, o = idx % CPH;
     float v = 0.f;
     if (c < C) {
@@ -183,7 +185,7 @@ STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const d
     }
     WcT[idx] = v;
   }
-  for (int o = tid; o < CPH; o += 256) {
+  for (int o = tid; o < CPH; o += nt) {
     float v = 0.f;
     if (o < C) v = k.bm[o];
     else if (o >= CP && o - CP < H) {
@@ -197,7 +199,24 @@ STG_DEVINL void block_prep_body(const BlkArgs& a, int z, int CP, int HP, const d
 __global__ void __launch_bounds__(256) k_block_prep(const BlkArgs a, int CP, int HP) {
   __shared__ double ssum[48], ssq[48];
   __shared__ float sa0[48], sc0[48], sWt[24 * 48];
-  block_prep_body(a, blockIdx.x, CP, HP, a.xmom, ssum, ssq, sa0, sc0, sWt);
+  block_prep_body(a, blockIdx.x, CP, HP, a.xmom, ssum, ssq, sa0, sc0, sWt, threadIdx.x, 256);
+}
+
+// both blocks' tables at once by one CTA of 256 threads: block z on threads [128 z, 128 z + 128)
+struct PrepScratch {
+  double ssum[2][48], ssq[2][48];
+  float sa0[2][48], sc0[2][48], sWt[2][24 * 48];
+};
+STG_DEVINL void block_prep_all(const BlkArgs& a, int CP, int HP, const double* xmom, PrepScratch& ps) {
+  if (a.nblk == 2 && CP <= 64) {
+    const int z = threadIdx.x >> 7;
+    block_prep_body(a, z, CP, HP, xmom, ps.ssum[z], ps.ssq[z], ps.sa0[z], ps.sc0[z], ps.sWt[z], threadIdx.x & 127, 128);
+  } else {
+    for (int z = 0; z < a.nblk; ++z) {
+      block_prep_body(a, z, CP, HP, xmom, ps.ssum[0], ps.ssq[0], ps.sa0[0], ps.sc0[0], ps.sWt[0], threadIdx.x, 256);
+      __syncthreads();
+    }
+  }
 }
 
 // x-moments and, in the last CTA to finish, the coefficient tables of every block: one launch
@@ -205,8 +224,7 @@ __global__ void __launch_bounds__(256) k_block_prep(const BlkArgs a, int CP, int
 __global__ void __launch_bounds__(256) k_xmoments_prep(const BlkArgs a, int CP, int HP, double* xmom,
                                                        unsigned* counter) {
   __shared__ float sm[2 * 48];
-  __shared__ double ssum[48], ssq[48];
-  __shared__ float sa0[48], sc0[48], sWt[24 * 48];
+  __shared__ PrepScratch ps;
   __shared__ int s_last;
   const int B = a.B, T = a.T, N = a.N, C = a.C;
   const int t = blockIdx.x, nb = gridDim.y;
@@ -238,10 +256,7 @@ __global__ void __launch_bounds__(256) k_xmoments_prep(const BlkArgs a, int CP, 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int z = 0; z < a.nblk; ++z) {
-    block_prep_body(a, z, CP, HP, xmom, ssum, ssq, sa0, sc0, sWt);
-    __syncthreads();
-  }
+  block_prep_all(a, CP, HP, xmom, ps);
 }
 
 // Same job for C == 16 (every reference hyper-parameter set with hidden_dim 8), without shared-memory atomics:
@@ -250,8 +265,7 @@ __global__ void __launch_bounds__(256) k_xmoments_prep(const BlkArgs a, int CP, 
 // l + 16 are folded with one shuffle and every warp issues 32 double atomics in all.  grid (ceil(T * wpt / 8)), 256.
 __global__ void __launch_bounds__(256) k_xmoments_prep16(const BlkArgs a, int CP, int HP, double* xmom,
                                                          unsigned* counter, int wpt) {
-  __shared__ double ssum[48], ssq[48];
-  __shared__ float sa0[48], sc0[48], sWt[24 * 48];
+  __shared__ PrepScratch ps;
   __shared__ int s_last;
   const int B = a.B, T = a.T, N = a.N;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -280,10 +294,7 @@ __global__ void __launch_bounds__(256) k_xmoments_prep16(const BlkArgs a, int CP
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int z = 0; z < a.nblk; ++z) {
-    block_prep_body(a, z, CP, HP, xmom, ssum, ssq, sa0, sc0, sWt);
-    __syncthreads();
-  }
+  block_prep_all(a, CP, HP, xmom, ps);
 }
 
 // BN0 statistics (batch or running), folded projection [Wm | Wtheta.diag(g0 r0)]^T and biases.

@@ -20,6 +20,14 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   const int tid = threadIdx.x, warp = tid >> 5;
 #ifdef STG_TC_TIMING
   if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][14] = clock64();
+  if (tid == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cta_time[blockIdx.x][0] = t;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_cta_time[blockIdx.x][2] = smid;
+  }
 #endif
   const int N = NT ? NT : a.N, M = 2 * N;
   const int C = a.C, T = a.T, H = k.H, s = k.stride, Lw = k.L;
@@ -326,19 +334,27 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   }
 
   // ---- CTA epilogue: parameter gradients, BN0 backward sums, dbtheta
-  __syncthreads();
-#pragma unroll
-  for (int h = 0; h < kHP; ++h) {
-    const float v = warp_sum(dbt_acc[h]), v2 = warp_sum(sov[h]);
-    if ((tid & 31) == 0) {
-      atomicAdd(&red[24 * 17 + h], v);
-      atomicAdd(&red[(kCP + h) * 17 + 16], v2);
-    }
-  }
+  //      per-warp partial column sums go to their own slots (no shared-memory atomics), one barrier, then they are
+  //      folded into column 16 of the G accumulator / the dbtheta slots
+  float* part = red + 24 * 17 + 8;      // [4 warps][32]: sof[16] | sov[8] | dbt[8]
 #pragma unroll
   for (int c = 0; c < kCP; ++c) {
     const float v = warp_sum(sof[c]);
-    if ((tid & 31) == 0) atomicAdd(&red[c * 17 + 16], v);
+    if ((tid & 31) == 0) part[warp * 32 + c] = v;
+  }
+#pragma unroll
+  for (int h = 0; h < kHP; ++h) {
+    const float v = warp_sum(sov[h]), v2 = warp_sum(dbt_acc[h]);
+    if ((tid & 31) == 0) {
+      part[warp * 32 + 16 + h] = v;
+      part[warp * 32 + 24 + h] = v2;
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const float v = (part[tid] + part[32 + tid]) + (part[64 + tid] + part[96 + tid]);
+    if (tid < 24) red[tid * 17 + 16] = v;          // column sums of [dF | dV]
+    else red[24 * 17 + (tid - 24)] = v;            // dbtheta
   }
   __syncthreads();
   const float* a0 = cst + kCstA0;
@@ -373,6 +389,11 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   __syncthreads();
 #ifdef STG_TC_TIMING
   if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][15] = clock64();
+  if (tid == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cta_time[blockIdx.x][1] = t;
+  }
 #endif
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
@@ -393,6 +414,9 @@ static void launch_bwd(const BlkArgs& a, int total, int n0, size_t smem, cudaStr
 }  // namespace tc
 
 #ifdef STG_TC_TIMING
+extern "C" int stg_debug_tc_cta_times_bwd(unsigned long long* out3072) {
+  return cudaMemcpyFromSymbol(out3072, tc::g_cta_time, sizeof(unsigned long long) * 3072) == cudaSuccess ? 0 : -1;
+}
 extern "C" int stg_debug_tc_stamps_bwd(long long* out32) {
   return cudaMemcpyFromSymbol(out32, tc::g_tc_stamp, sizeof(long long) * 32) == cudaSuccess ? 0 : -1;
 }

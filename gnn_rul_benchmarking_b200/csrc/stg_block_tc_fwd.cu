@@ -28,6 +28,14 @@ __global__ void __launch_bounds__(128, WR == 32 ? 4 : 2) k_block_fwd_tc(const Bl
   const int tid = threadIdx.x, warp = tid >> 5;
 #ifdef STG_TC_TIMING
   if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][14] = clock64();
+  if (tid == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cta_time[blockIdx.x][0] = t;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_cta_time[blockIdx.x][2] = smid;
+  }
 #endif
   const int N = NT ? NT : a.N, M = 2 * N;
   const int C = a.C, T = a.T, H = k.H, s = k.stride, Lw = k.L;
@@ -255,29 +263,42 @@ __global__ void __launch_bounds__(128, WR == 32 ? 4 : 2) k_block_fwd_tc(const Bl
     STG_STAMP(13)
   }
 
+#ifdef STG_TC_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][10] = clock64();
+#endif
   if (TRAIN) {
-    float* red = cst + kCstRed;
-    __syncthreads();
-    if (tid < 2 * kHP) red[tid] = 0.f;
-    __syncthreads();
+    // per-warp partial moments in their own slots (no shared-memory atomics: float atomics on shared memory are CAS
+    // loops on sm_100a), one barrier, then one double atomic per feature and CTA
+    float* part = cst + kCstRed;        // [4 warps][16]
 #pragma unroll
     for (int h = 0; h < kHP; ++h) {
       const float v1 = warp_sum(st1[h]), v2 = warp_sum(st2[h]);
       if ((tid & 31) == 0) {
-        atomicAdd(&red[h], v1);
-        atomicAdd(&red[kHP + h], v2);
+        part[warp * 16 + h] = v1;
+        part[warp * 16 + kHP + h] = v2;
       }
     }
     __syncthreads();
-    if (tid < H) {
-      atomicAdd(&k.stats[tid], (double)red[tid]);
-      atomicAdd(&k.stats[H + tid], (double)red[kHP + tid]);
+    if (tid < 2 * kHP) {
+      const int h = tid & (kHP - 1);
+      if (h < H) {
+        const float v = (part[tid] + part[16 + tid]) + (part[32 + tid] + part[48 + tid]);
+        atomicAdd(&k.stats[(tid < kHP ? 0 : H) + h], (double)v);
+      }
     }
   }
+#ifdef STG_TC_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][11] = clock64();
+#endif
   tc_fence_before();
   __syncthreads();
 #ifdef STG_TC_TIMING
   if (blockIdx.x == 0 && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][15] = clock64();
+  if (tid == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cta_time[blockIdx.x][1] = t;
+  }
 #endif
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
@@ -300,6 +321,9 @@ static void launch_fwd(const BlkArgs& a, int total, int n0, size_t smem, cudaStr
 }  // namespace tc
 
 #ifdef STG_TC_TIMING
+extern "C" int stg_debug_tc_cta_times_fwd(unsigned long long* out3072) {
+  return cudaMemcpyFromSymbol(out3072, tc::g_cta_time, sizeof(unsigned long long) * 3072) == cudaSuccess ? 0 : -1;
+}
 extern "C" int stg_debug_tc_stamps_fwd(long long* out32) {
   return cudaMemcpyFromSymbol(out32, tc::g_tc_stamp, sizeof(long long) * 32) == cudaSuccess ? 0 : -1;
 }

@@ -154,8 +154,8 @@ constexpr int kCstBn1 = 32;        // [7][8]
 constexpr int kCstBt = 88;         // [8]
 constexpr int kCstA0 = 96;         // a0[16] c0[16] mu0[16] r0[16]
 constexpr int kCstMisc = 160;      // decay
-constexpr int kCstRed = 176;       // reductions at CTA end: up to 24*17 + 16 floats
-constexpr int kCstFloats = 176 + 24 * 17 + 32;
+constexpr int kCstRed = 176;       // backward: G[24][17], dbt[8], per-warp partials [4][32]; forward: partials [4][16]
+constexpr int kCstFloats = 176 + 24 * 17 + 8 + 128 + 8;
 
 __host__ __device__ inline SmemLayout make_layout(int WR, bool bwd, bool split) {
   SmemLayout l;
@@ -416,6 +416,7 @@ inline int sm_count() {
 #ifdef STG_TC_TIMING
 // debug build only (-DSTG_TC_TIMING): clock64 stamps of CTA 0's second tile, threads 0 and 64
 static __device__ long long g_tc_stamp[2][16];          // per translation unit: [thread 0 | 64][stamp]
+static __device__ unsigned long long g_cta_time[1024][3];  // globaltimer at CTA start / end, SM id
 #define STG_STAMP(n)                                                                              \
   if (blockIdx.x == 0 && tile == cta + ncta && (tid == 0 || tid == 64)) g_tc_stamp[tid == 64][n] = clock64();
 #else

@@ -35,10 +35,13 @@ for kern in (0, 1):
     prev = [buf[base], buf[base + 16]]
     for i in range(1, 14):
         cur = [buf[base + i], buf[base + 16 + i]]
-        if cur[0] <= 0:
+        if cur[0] <= 0 or (kern == 0 and i in (10, 11)):
             continue
         print(f"  {names[kern][i]:14s} +{cur[0] - prev[0]:6d} | +{cur[1] - prev[1]:6d}")
         prev = cur
     print(f"  total {prev[0] - buf[base]}")
+    if kern == 0:
+        print(f"  CTA 0 forward: kernel start -> tile-loop end {buf[base + 10] - buf[base + 14]}, reductions + atomics "
+              f"{buf[base + 11] - buf[base + 10]}, -> kernel end {buf[base + 15] - buf[base + 11]}")
     print(f"  CTA 0: kernel start -> this (2nd) tile start {buf[base] - buf[base + 14]}, tile end -> kernel end {buf[base + 15] - buf[base + 13]}, "
           f"whole CTA {buf[base + 15] - buf[base + 14]}")
