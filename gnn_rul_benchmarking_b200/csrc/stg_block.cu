@@ -264,28 +264,46 @@ __global__ void __launch_bounds__(256) k_xmoments_prep(const BlkArgs a, int CP, 
 // (the slab is read as consecutive floats and 32 % 16 == 0), so the moments stay in two registers per lane, lanes l and
 // l + 16 are folded with one shuffle and every warp issues 32 double atomics in all.  grid (ceil(T * wpt / 8)), 256.
 __global__ void __launch_bounds__(256) k_xmoments_prep16(const BlkArgs a, int CP, int HP, double* xmom,
-                                                         unsigned* counter, int wpt) {
+                                                         unsigned* counter, int nslice) {
   __shared__ PrepScratch ps;
+  __shared__ float red[8][32];
   __shared__ int s_last;
   const int B = a.B, T = a.T, N = a.N;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (gw < T * wpt) {
-    const int t = gw % T, sl = gw / T;
+  const int t = blockIdx.x % T, sl = blockIdx.x / T;         // CTA = (time step, batch slice); warp = sample stride
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
     const int NC = N * 16;
     float s1 = 0.f, s2 = 0.f;
-    for (int b = sl; b < B; b += wpt) {
+    for (int b = sl * 8 + warp; b < B; b += nslice * 8) {
       const float* p = a.x + ((size_t)b * T + t) * NC;
-      for (int e = lane; e < NC; e += 32) {
-        const float v = __ldg(p + e);
-        s1 += v;
-        s2 = fmaf(v, v, s2);
+      // all loads of the slab first (independent), then the sums: the kernel is latency bound
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = (lane + 32 * u < NC) ? __ldg(p + lane + 32 * u) : 0.f;
+      for (int e = lane + 512; e < NC; e += 32) {           // N > 32 sensors: the rest of the slab
+        const float w = __ldg(p + e);
+        s1 += w;
+        s2 = fmaf(w, w, s2);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        s1 += v[u];
+        s2 = fmaf(v[u], v[u], s2);
       }
     }
     s1 += __shfl_down_sync(0xffffffffu, s1, 16);
     s2 += __shfl_down_sync(0xffffffffu, s2, 16);
     if (lane < 16) {
-      atomicAdd(&xmom[t * 16 + lane], (double)s1);
-      atomicAdd(&xmom[(size_t)T * 16 + t * 16 + lane], (double)s2);
+      red[warp][lane] = s1;
+      red[warp][16 + lane] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+      const int c = threadIdx.x & 15;
+      atomicAdd(&xmom[(threadIdx.x < 16 ? 0 : (size_t)T * 16) + t * 16 + c], (double)v);
     }
   }
   __threadfence();
@@ -1256,12 +1274,11 @@ int launch_xmoments_prep(const BlkArgs& a, const BlkPlan& p, double* xmom, unsig
   if (nb > 64) nb = 64;
   ProfScope ps(kProfXmoments, s);
   if (a.C == 16 && !getenv("STG_XMOM_GENERIC")) {
-    // warps per time step: enough warps for ~8 per SM, at most one per sample
-    int wpt = (148 * 8 + a.T - 1) / a.T;
-    if (wpt > a.B) wpt = a.B;
-    if (wpt < 1) wpt = 1;
-    const int warps = a.T * wpt;
-    k_xmoments_prep16<<<(warps + 7) / 8, 256, 0, s>>>(a, p.CP, p.HP, xmom, counter, wpt);
+    // batch slices per time step: ~4 CTAs of 8 warps per SM, at most one sample per warp
+    int nslice = (148 * 4 + a.T - 1) / a.T;
+    if (nslice * 8 > a.B) nslice = (a.B + 7) / 8;
+    if (nslice < 1) nslice = 1;
+    k_xmoments_prep16<<<a.T * nslice, 256, 0, s>>>(a, p.CP, p.HP, xmom, counter, nslice);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
   }
   k_xmoments_prep<<<dim3(a.T, nb), 256, 0, s>>>(a, p.CP, p.HP, xmom, counter);
