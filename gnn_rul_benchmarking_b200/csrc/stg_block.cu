@@ -1235,8 +1235,6 @@ int plan_blocks(BlkArgs& a, BlkPlan& p, char* err, size_t errlen) {
       }
     if (!done) { snprintf(err, errlen, "backward tile does not fit shared memory"); return -2; }
   }
-  // tensor-core backward is opt-in (STG_MMA_BWD=1): at 1 CTA/SM it does not beat the SIMT kernel yet
-  if (!getenv("STG_NO_MMA") && getenv("STG_MMA_BWD")) plan_blocks_mma_bwd(a, p);
   // Blackwell path: tcgen05.mma + TMEM for both directions whenever the shape fits (overrides the above)
   if (plan_blocks_tc(a, p)) {
     p.mma_f = 0; p.mma_b = 0;
@@ -1353,8 +1351,6 @@ int launch_block_backward(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   }
   if (p.tc) {
     launch_block_backward_tc(a, p, s);
-  } else if (p.mma_b) {
-    launch_block_backward_mma(a, p, s);
   } else {
     ProfScope ps(kProfBwdMain, s);
     v->bwd<<<dim3(p.grid_x_b, a.B, a.nblk), p.threads_b, p.smem_b, s>>>(a, rows_max, p.wpc_b, slot);

@@ -87,9 +87,7 @@ inline int bwd_rows_exact(const BlkArgs& a, int* max_windows = nullptr) {
 
 // tensor-core path (stg_block_mma.cu)
 bool plan_blocks_mma_fwd(BlkArgs& a, BlkPlan& p);
-bool plan_blocks_mma_bwd(BlkArgs& a, BlkPlan& p);
 int launch_block_forward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
-int launch_block_backward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s);
 
 // tcgen05 / TMEM path (stg_block_tc.cu)
 bool plan_blocks_tc(BlkArgs& a, BlkPlan& p);

@@ -465,432 +465,14 @@ __global__ void __launch_bounds__(256) k_block_fwd_mma(const BlkArgs a, int rows
 // ------------------------------------------------------------------------------------------
 // backward: one CTA = (chunk of time steps [ta,tb), sample b, block z); one warp = one window
 // ------------------------------------------------------------------------------------------
-template <int CP, int HP, int NT>
-struct BwdTile {
-  static constexpr int NH = HP / 8, MP = NT * 8;
-  // Pass A of m-tile MT: S, P, dY' (-> dY planes), dA, dS (kept in registers), A~ -> As.
-  template <int MT>
-  static STG_DEVINL void pass_a(const BlkDev& k, const float* Fh, const float* Fl, int FVP, int M, int N, int H, int g,
-                                int t, const LaneCols<NT>& lc, const float* pw, const float* bn1c, const float* yrow,
-                                const float* drow, float invw, bool own_win, float* As, int SP, float* dYh,
-                                float* dYl, int DP, float (&ds)[NT][4], float (&dbt)[NH][2]) {
-    if (MT * 16 >= M) return;
-    const int r0 = MT * 16 + g, r1 = r0 + 8;
-    float p[NT][4];
-    unsigned sgn;
-    s_tile_softmax<CP, NT, MT, true>(Fh, Fl, FVP, M, g, t, lc.dj, p, sgn);
-    // dY' of rows r0, r1 for this lane's columns (k-permuted pair h = q*8 + 2t, +1)
-    FragA fdy[NH];
-#pragma unroll
-    for (int q = 0; q < NH; ++q) {
-      float dy[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int h = q * 8 + 2 * t + (u & 1), row = (u < 2) ? r0 : r1;
-        float v = 0.f;
-        if (h < H && row < M) {
-          const int nn = row % N;
-          const float yv = yrow[(size_t)row * H + h];
-          const float yn = fmaf(bn1c[h], yv, bn1c[HP + h]);
-          const float dyn = drow[nn * H + h] * invw * (yn > 0.f ? 1.f : kLeaky);
-          const float yh = (yv - bn1c[2 * HP + h]) * bn1c[3 * HP + h];
-          v = bn1c[4 * HP + h] * dyn - bn1c[5 * HP + h] - yh * bn1c[6 * HP + h];
-          if (own_win) dbt[q][u & 1] += v;
-        }
-        dy[u] = v;
-      }
-      fdy[q] = frag_a_split(dy[0], dy[2], dy[1], dy[3]);
-      const int c = q * 8 + 2 * t;
-      *reinterpret_cast<uint2*>(dYh + r0 * DP + c) = make_uint2(fdy[q].hi[0], fdy[q].hi[2]);
-      *reinterpret_cast<uint2*>(dYl + r0 * DP + c) = make_uint2(fdy[q].lo[0], fdy[q].lo[2]);
-      *reinterpret_cast<uint2*>(dYh + r1 * DP + c) = make_uint2(fdy[q].hi[1], fdy[q].hi[3]);
-      *reinterpret_cast<uint2*>(dYl + r1 * DP + c) = make_uint2(fdy[q].lo[1], fdy[q].lo[3]);
-    }
-    // dA = dY' . V^T   (B[k=h][n=col] = V[col][h], pair adjacent in the row)
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      ds[n][0] = ds[n][1] = ds[n][2] = ds[n][3] = 0.f;
-#pragma unroll
-      for (int q = 0; q < NH; ++q) mma3(ds[n], fdy[q], frag_b_pair(Fh, Fl, FVP, n * 8 + g, CP + q * 8 + 2 * t));
-    }
-    // dP = dA.*mask ; rs = rowsum(dP.*P) ; dLam = P.*(dP - rs) ; dS = dLam.*lrelu'(S) ; A~ = P.*mask + I
-    const int tr0 = r0 / N, tr1 = r1 / N;
-    float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const float m00 = mask_val(pw, tr0, lc.tcol[n][0]), m01 = mask_val(pw, tr0, lc.tcol[n][1]);
-      const float m10 = mask_val(pw, tr1, lc.tcol[n][0]), m11 = mask_val(pw, tr1, lc.tcol[n][1]);
-      ds[n][0] *= m00; ds[n][1] *= m01; ds[n][2] *= m10; ds[n][3] *= m11;
-      rs0 = fmaf(ds[n][0], p[n][0], rs0); rs0 = fmaf(ds[n][1], p[n][1], rs0);
-      rs1 = fmaf(ds[n][2], p[n][2], rs1); rs1 = fmaf(ds[n][3], p[n][3], rs1);
-      float a0 = p[n][0] * m00, a1 = p[n][1] * m01, a2 = p[n][2] * m10, a3 = p[n][3] * m11;
-      if (n == 2 * MT) { if (lc.dj == 0) a0 += 1.f; if (lc.dj == 1) a1 += 1.f; }
-      if (n == 2 * MT + 1) { if (lc.dj == 0) a2 += 1.f; if (lc.dj == 1) a3 += 1.f; }
-      const int c = n * 8 + 2 * t;
-      *reinterpret_cast<float2*>(As + r0 * SP + c) = make_float2(a0, a1);
-      *reinterpret_cast<float2*>(As + r1 * SP + c) = make_float2(a2, a3);
-    }
-    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
-    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
-    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
-    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      ds[n][0] = p[n][0] * (ds[n][0] - rs0) * ((sgn >> (n * 4 + 0)) & 1u ? 1.f : kLeaky);
-      ds[n][1] = p[n][1] * (ds[n][1] - rs0) * ((sgn >> (n * 4 + 1)) & 1u ? 1.f : kLeaky);
-      ds[n][2] = p[n][2] * (ds[n][2] - rs1) * ((sgn >> (n * 4 + 2)) & 1u ? 1.f : kLeaky);
-      ds[n][3] = p[n][3] * (ds[n][3] - rs1) * ((sgn >> (n * 4 + 3)) & 1u ? 1.f : kLeaky);
-    }
-  }
-
-  template <int MT>
-  static STG_DEVINL void store_ds(int M, int g, int t, float* Ds, int SP, const float (&ds)[NT][4]) {
-    if (MT * 16 >= M) return;
-    const int r0 = MT * 16 + g, r1 = r0 + 8;
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const int c = n * 8 + 2 * t;
-      *reinterpret_cast<float2*>(Ds + r0 * SP + c) = make_float2(ds[n][0], ds[n][1]);
-      *reinterpret_cast<float2*>(Ds + r1 * SP + c) = make_float2(ds[n][2], ds[n][3]);
-    }
-  }
-
-  // dV tile (rows k = MT*16+g,+8) = sum_i A~[i][k] dY'[i][:]  -> atomics into dFV[:, CP:]
-  template <int MT>
-  static STG_DEVINL void pass_dv(int M, int H, int g, int t, const float* As, int SP, const float* dYh,
-                                 const float* dYl, int DP, float* dfv, int FVP) {
-    if (MT * 16 >= M) return;
-    const int r0 = MT * 16 + g, r1 = r0 + 8;
-    const int MTE = (M + 15) / 16;
-    float acc[NH][4];
-#pragma unroll
-    for (int q = 0; q < NH; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
-#pragma unroll
-    for (int kt = 0; kt < NT; ++kt) {
-      if (kt < 2 * MTE) {                       // rows i beyond the last m-tile were never written
-        const int i0 = kt * 8 + 2 * t;
-        const FragA fa = frag_a_split(As[i0 * SP + r0], As[i0 * SP + r1], As[(i0 + 1) * SP + r0], As[(i0 + 1) * SP + r1]);
-#pragma unroll
-        for (int q = 0; q < NH; ++q) mma3(acc[q], fa, frag_b_rows(dYh, dYl, DP, i0, q * 8 + g));
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < NH; ++q)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int h = q * 8 + 2 * t + (u & 1), row = (u < 2) ? r0 : r1;
-        if (h < H && row < M) atomicAdd(&dfv[row * FVP + CP + h], acc[q][u]);
-      }
-  }
-
-  // dF tile (rows MT*16+g,+8) = sum_k (dS[r][k] + dS[k][r]) F[k][:]  -> atomics into dFV[:, 0:CP]
-  template <int MT>
-  static STG_DEVINL void pass_df(const float* Fh, const float* Fl, int FVP, int M, int C, int g, int t, const float* Ds,
-                                 int SP, float* dfv) {
-    if (MT * 16 >= M) return;
-    constexpr int NC = CP / 8;
-    const int r0 = MT * 16 + g, r1 = r0 + 8;
-    const int MTE = (M + 15) / 16;
-    float acc[NC][4];
-#pragma unroll
-    for (int n = 0; n < NC; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-#pragma unroll
-    for (int kt = 0; kt < NT; ++kt) {
-      if (kt < 2 * MTE) {
-        const int k0 = kt * 8 + 2 * t;
-        const float2 d0 = ldf2(Ds + r0 * SP + k0), d1 = ldf2(Ds + r1 * SP + k0);
-        const FragA fa = frag_a_split(d0.x + Ds[k0 * SP + r0], d1.x + Ds[k0 * SP + r1],
-                                      d0.y + Ds[(k0 + 1) * SP + r0], d1.y + Ds[(k0 + 1) * SP + r1]);
-#pragma unroll
-        for (int n = 0; n < NC; ++n) mma3(acc[n], fa, frag_b_rows(Fh, Fl, FVP, k0, n * 8 + g));
-      }
-    }
-#pragma unroll
-    for (int n = 0; n < NC; ++n)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = n * 8 + 2 * t + (u & 1), row = (u < 2) ? r0 : r1;
-        if (c < C && row < M) atomicAdd(&dfv[row * FVP + c], acc[n][u]);
-      }
-  }
-};
-
-template <int CP, int HP, int NT>
-__global__ void __launch_bounds__(256) k_block_bwd_mma(const BlkArgs a, int rows_max) {
-  constexpr int CPH = CP + HP, MP = NT * 8, NH = HP / 8, NC = CP / 8, MTM = NT / 2;
-  extern __shared__ __align__(16) unsigned char smraw[];
-  const BlkDev& k = a.b[blockIdx.z];
-  const int chunk = blockIdx.x;
-  if (chunk >= k.nchunk_b) return;
-  const int b = blockIdx.y;
-  const int N = a.N, C = a.C, T = a.T, H = k.H, w = k.w, s = k.stride, L = k.L, M = w * N;
-  int per = (T + k.nchunk_b - 1) / k.nchunk_b;
-  per = ((per + s - 1) / s) * s;                       // chunk boundaries on window starts
-  const int ta = chunk * per, tb = min(T, ta + per);
-  if (ta >= tb) return;
-  int l_lo = ta - (w - 1);
-  l_lo = l_lo <= 0 ? 0 : (l_lo + s - 1) / s;
-  const int l_hi = min(L - 1, (tb - 1) / s);
-  const bool any_win = l_lo <= l_hi;
-  const int t_lo = any_win ? min(ta, l_lo * s) : ta;
-  const int t_hi = any_win ? max(tb - 1, l_hi * s + w - 1) : tb - 1;
-  const int rows = (t_hi - t_lo + 1) * N;
-  const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, nw = nthr >> 5, lane = tid & 31, g = lane >> 2,
-            t = lane & 3;
-
-  const MLay lay = make_mlay(CP, HP, MP, M, C, rows_max, nw, 2);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smraw);
-  float* sm = reinterpret_cast<float*>(smraw + 16);
-  float* tab = sm + lay.tab;
-  float* bn1c = sm + lay.bn1c;
-  float* red = sm + lay.red;       // [0,CP) sb  [CP,2CP) sg  [2CP, 2CP+HP) dbt
-  float* Gs = sm + lay.gs;         // [up16(CPH)+1][CP] parameter-gradient tile, then so[CPH]
-  float* fhi = sm + lay.fhi;
-  float* flo = sm + lay.flo;
-  float* dfv = sm + lay.dfv;
-  const int FVP = lay.FVP, SP = lay.SP, DP = lay.DP, WP = lay.WP;
-  const float* pw = tab + 4 * CP + CPH;
-  const float *mu0 = tab, *r0c = tab + CP, *a0 = tab + 2 * CP, *c0 = tab + 3 * CP;
-
-  if (tid == 0) mbar_init(bar, 1);
-  __syncthreads();
-  const int shift = stage_floats_tma(sm + lay.xs, a.x + ((size_t)b * T + t_lo) * N * C, rows * C, bar, tid);
-  float* xs = sm + lay.xs + shift;
-  load_table<CP, HP, true>(a, k, tab);
-  // raw Wm [o][c], Wtheta [h][c] as hi/lo planes (B operands of the tail products)
-  for (int idx = tid; idx < CP * CP; idx += nthr) {
-    const int o = idx / CP, c = idx - o * CP;
-    uint32_t h, l;
-    split2((o < C && c < C) ? k.Wm[o * C + c] : 0.f, h, l);
-    sm[lay.wmh + o * WP + c] = __uint_as_float(h);
-    sm[lay.wml + o * WP + c] = __uint_as_float(l);
-  }
-  for (int idx = tid; idx < HP * CP; idx += nthr) {
-    const int hh = idx / CP, c = idx - hh * CP;
-    uint32_t h, l;
-    split2((hh < H && c < C) ? k.Wt[hh * C + c] : 0.f, h, l);
-    sm[lay.wth + hh * WP + c] = __uint_as_float(h);
-    sm[lay.wtl + hh * WP + c] = __uint_as_float(l);
-  }
-  // BN1 backward coefficients: [0]=a1 [1]=c1 [2]=mu1 [3]=r1 [4]=g1*r1 [5]=q1 [6]=q2
-  if (tid < HP) {
-    float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (tid < H) {
-      const int h = tid;
-      const double R = (double)a.B * L * M;
-      const double m = k.stats[h] / R;
-      double var = k.stats[H + h] / R - m * m;
-      if (var < 0.0) var = 0.0;
-      const float r1 = (float)(1.0 / sqrt(var + (double)a.eps));
-      const float g1 = k.g1[h];
-      v[0] = g1 * r1;
-      v[1] = k.b1[h] - v[0] * (float)m;
-      v[2] = (float)m;
-      v[3] = r1;
-      v[4] = g1 * r1;
-      v[5] = (float)(g1 * k.stats[2 * H + h] / R) * r1;
-      v[6] = (float)(g1 * k.stats[3 * H + h] / R) * r1;
-    }
-#pragma unroll
-    for (int q = 0; q < 7; ++q) bn1c[q * HP + tid] = v[q];
-  }
-  for (int i = tid; i < 2 * CP + 4 * HP + 4; i += nthr) red[i] = 0.f;
-  for (int i = tid; i < (up16(CPH) + 1) * CP + CPH + 4; i += nthr) Gs[i] = 0.f;
-  for (int i = tid; i < lay.rows_alloc * FVP + 8; i += nthr) dfv[i] = 0.f;
-  for (int i = rows * FVP + tid; i < lay.rows_alloc * FVP + 8; i += nthr) { fhi[i] = 0.f; flo[i] = 0.f; }
-  __syncthreads();
-  split_weights<CP, HP>(tab, sm + lay.whi, sm + lay.wlo, FVP);
-  mbar_wait(bar, 0);
-  for (int i = rows * C + tid; i < up16(rows) * C; i += nthr) xs[i] = 0.f;
-  __syncthreads();
-  project_fv<CP, HP>(tab, sm + lay.whi, sm + lay.wlo, xs, fhi, flo, FVP, rows, C);
-  __syncthreads();
-
-  const LaneCols<NT> lc = make_lane_cols<NT>(g, t, N);
-  float* As = sm + lay.scr + warp * lay.scr_per_warp;      // [MP][SP]: A~, then dS
-  float* dYh = As + MP * SP;                               // [MP][DP]
-  float* dYl = dYh + MP * DP;
-  const float invw = 1.f / (float)w;
-  float dbt[NH][2];
-#pragma unroll
-  for (int q = 0; q < NH; ++q) dbt[q][0] = dbt[q][1] = 0.f;
-  using Tile = BwdTile<CP, HP, NT>;
-
-  if (any_win)
-    for (int l = l_lo + warp; l <= l_hi; l += nw) {
-      const int row0 = (l * s - t_lo) * N;
-      const float* Fh = fhi + (size_t)row0 * FVP;
-      const float* Fl = flo + (size_t)row0 * FVP;
-      float* dfw = dfv + (size_t)row0 * FVP;
-      const float* yrow = k.yp + ((size_t)b * L + l) * M * H;
-      const float* drow = k.dout + (size_t)b * k.dout_bs + (size_t)l * N * H;
-      const bool own_win = (l * s >= ta) && (l * s < tb);
-      float ds[MTM][NT][4];
-      Tile::template pass_a<0>(k, Fh, Fl, FVP, M, N, H, g, t, lc, pw, bn1c, yrow, drow, invw, own_win, As, SP, dYh, dYl,
-                               DP, ds[0], dbt);
-      if (MTM > 1) Tile::template pass_a<(MTM > 1 ? 1 : 0)>(k, Fh, Fl, FVP, M, N, H, g, t, lc, pw, bn1c, yrow, drow, invw,
-                                                            own_win, As, SP, dYh, dYl, DP, ds[MTM > 1 ? 1 : 0], dbt);
-      if (MTM > 2) Tile::template pass_a<(MTM > 2 ? 2 : 0)>(k, Fh, Fl, FVP, M, N, H, g, t, lc, pw, bn1c, yrow, drow, invw,
-                                                            own_win, As, SP, dYh, dYl, DP, ds[MTM > 2 ? 2 : 0], dbt);
-      if (MTM > 3) Tile::template pass_a<(MTM > 3 ? 3 : 0)>(k, Fh, Fl, FVP, M, N, H, g, t, lc, pw, bn1c, yrow, drow, invw,
-                                                            own_win, As, SP, dYh, dYl, DP, ds[MTM > 3 ? 3 : 0], dbt);
-      __syncwarp();
-      Tile::template pass_dv<0>(M, H, g, t, As, SP, dYh, dYl, DP, dfw, FVP);
-      if (MTM > 1) Tile::template pass_dv<1>(M, H, g, t, As, SP, dYh, dYl, DP, dfw, FVP);
-      if (MTM > 2) Tile::template pass_dv<2>(M, H, g, t, As, SP, dYh, dYl, DP, dfw, FVP);
-      if (MTM > 3) Tile::template pass_dv<3>(M, H, g, t, As, SP, dYh, dYl, DP, dfw, FVP);
-      __syncwarp();
-      Tile::template store_ds<0>(M, g, t, As, SP, ds[0]);
-      if (MTM > 1) Tile::template store_ds<1>(M, g, t, As, SP, ds[MTM > 1 ? 1 : 0]);
-      if (MTM > 2) Tile::template store_ds<2>(M, g, t, As, SP, ds[MTM > 2 ? 2 : 0]);
-      if (MTM > 3) Tile::template store_ds<3>(M, g, t, As, SP, ds[MTM > 3 ? 3 : 0]);
-      __syncwarp();
-      Tile::template pass_df<0>(Fh, Fl, FVP, M, C, g, t, As, SP, dfw);
-      if (MTM > 1) Tile::template pass_df<1>(Fh, Fl, FVP, M, C, g, t, As, SP, dfw);
-      if (MTM > 2) Tile::template pass_df<2>(Fh, Fl, FVP, M, C, g, t, As, SP, dfw);
-      if (MTM > 3) Tile::template pass_df<3>(Fh, Fl, FVP, M, C, g, t, As, SP, dfw);
-      __syncwarp();
-    }
-  // dbt: reduce over the row groups
-#pragma unroll
-  for (int q = 0; q < NH; ++q)
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float v = dbt[q][u];
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (g == 0) atomicAdd(&red[2 * CP + q * 8 + 2 * t + u], v);
-    }
-  __syncthreads();
-
-  // ---------------- tail over the owned rows [r_beg, r_end) ----------------
-  const int r_beg = (ta - t_lo) * N, r_end = (tb - t_lo) * N, nown = r_end - r_beg;
-  {
-    // (a) dx partial = dF.Wm + a0 .* (dV.Wtheta);  BN0 sums  sb = sum dXb, sg = sum dXb*xhat
-    float sb[NC][2], sg[NC][2];
-#pragma unroll
-    for (int n = 0; n < NC; ++n) sb[n][0] = sb[n][1] = sg[n][0] = sg[n][1] = 0.f;
-    float* dxp = k.dxp + ((size_t)b * T + ta) * N * C;
-    const int ntile = (nown + 15) / 16;
-    for (int mt = warp; mt < ntile; mt += nw) {
-      const int q0 = r_beg + mt * 16 + g, q1 = q0 + 8;       // rows in the staged slab
-      float pf[NC][4], dxb[NC][4];
-#pragma unroll
-      for (int n = 0; n < NC; ++n)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) pf[n][u] = dxb[n][u] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < NC; ++kk) {
-        const int kc = kk * 8 + 2 * t;
-        const float2 d0 = ldf2(dfv + q0 * FVP + kc), d1 = ldf2(dfv + q1 * FVP + kc);
-        const FragA fa = frag_a_split(d0.x, d1.x, d0.y, d1.y);
-#pragma unroll
-        for (int n = 0; n < NC; ++n) mma3(pf[n], fa, frag_b_rows(sm + lay.wmh, sm + lay.wml, WP, kc, n * 8 + g));
-      }
-#pragma unroll
-      for (int kk = 0; kk < NH; ++kk) {
-        const int kc = kk * 8 + 2 * t;
-        const float2 d0 = ldf2(dfv + q0 * FVP + CP + kc), d1 = ldf2(dfv + q1 * FVP + CP + kc);
-        const FragA fa = frag_a_split(d0.x, d1.x, d0.y, d1.y);
-#pragma unroll
-        for (int n = 0; n < NC; ++n) mma3(dxb[n], fa, frag_b_rows(sm + lay.wth, sm + lay.wtl, WP, kc, n * 8 + g));
-      }
-#pragma unroll
-      for (int n = 0; n < NC; ++n)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = n * 8 + 2 * t + (u & 1), q = (u < 2) ? q0 : q1;
-          if (c < C && q < r_end) {
-            const float dv = dxb[n][u];
-            const float xh = (xs[q * C + c] - mu0[c]) * r0c[c];
-            sb[n][u & 1] += dv;
-            sg[n][u & 1] = fmaf(dv, xh, sg[n][u & 1]);
-            dxp[(size_t)(q - r_beg) * C + c] = fmaf(dv, a0[c], pf[n][u]);
-          }
-        }
-    }
-#pragma unroll
-    for (int n = 0; n < NC; ++n)
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float v1 = sb[n][u], v2 = sg[n][u];
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-          v2 += __shfl_xor_sync(0xffffffffu, v2, o);
-        }
-        if (g == 0) {
-          atomicAdd(&red[n * 8 + 2 * t + u], v1);
-          atomicAdd(&red[CP + n * 8 + 2 * t + u], v2);
-        }
-      }
-  }
-  {
-    // (b) G[o][c] = sum_rows dFV[r][o] * x[r][c]  (o over [F | V] columns), k-steps split over the warps
-    constexpr int MTO = (CPH + 15) / 16;
-    const int nks = (nown + 7) / 8;
-#pragma unroll 1
-    for (int mo = 0; mo < MTO; ++mo) {
-      float acc[NC][4];
-#pragma unroll
-      for (int n = 0; n < NC; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      const int o0 = mo * 16 + g, o1 = o0 + 8;
-      for (int ks = warp; ks < nks; ks += nw) {
-        const int q = r_beg + ks * 8 + 2 * t;
-        const bool v0 = q < r_end, v1 = q + 1 < r_end;
-        const FragA fa = frag_a_split(v0 ? dfv[q * FVP + o0] : 0.f, v0 ? dfv[q * FVP + o1] : 0.f,
-                                      v1 ? dfv[(q + 1) * FVP + o0] : 0.f, v1 ? dfv[(q + 1) * FVP + o1] : 0.f);
-#pragma unroll
-        for (int n = 0; n < NC; ++n)
-          mma3(acc[n], fa, frag_b_split(v0 ? xs[q * C + n * 8 + g] : 0.f, v1 ? xs[(q + 1) * C + n * 8 + g] : 0.f));
-      }
-#pragma unroll
-      for (int n = 0; n < NC; ++n)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = n * 8 + 2 * t + (u & 1), o = (u < 2) ? o0 : o1;
-          atomicAdd(&Gs[o * CP + c], acc[n][u]);
-        }
-    }
-    // column sums so[o] = sum_rows dFV[r][o]
-    float* so = Gs + (up16(CPH) + 1) * CP;
-    for (int idx = tid; idx < CPH * 8; idx += nthr) {
-      const int o = idx % CPH, sl = idx / CPH;
-      float v = 0.f;
-      for (int r = r_beg + sl; r < r_end; r += 8) v += dfv[r * FVP + o];
-      atomicAdd(&so[o], v);
-    }
-  }
-  __syncthreads();
-  {
-    const float* so = Gs + (up16(CPH) + 1) * CP;
-    for (int idx = tid; idx < CPH * C; idx += nthr) {
-      const int o = idx / C, c = idx - o * C;
-      const bool isF = o < C, isV = (o >= CP && o - CP < H);
-      if (!isF && !isV) continue;
-      const float gv = Gs[o * CP + c];
-      if (isF) {
-        atomicAdd(&k.dWm[o * C + c], gv);
-        if (c == 0) atomicAdd(&k.dbm[o], so[o]);
-      } else {
-        atomicAdd(&k.dWt[(o - CP) * C + c], fmaf(a0[c], gv, c0[c] * so[o]));
-      }
-    }
-    if (tid < C) {
-      atomicAdd(&k.stats[4 * H + tid], (double)red[tid]);
-      atomicAdd(&k.stats[4 * H + C + tid], (double)red[CP + tid]);
-    }
-    if (tid < H) atomicAdd(&k.dbt[tid], red[2 * CP + tid]);
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------
 typedef void (*MK)(const BlkArgs, int);
-struct MVariant { int CP, HP, NT; MK fwd_train, fwd_eval, bwd; };
+struct MVariant { int CP, HP, NT; MK fwd_train, fwd_eval; };
 #define STG_MV(CP, HP, NT) \
-  { CP, HP, NT, k_block_fwd_mma<CP, HP, NT, true>, k_block_fwd_mma<CP, HP, NT, false>, k_block_bwd_mma<CP, HP, NT> }
+  { CP, HP, NT, k_block_fwd_mma<CP, HP, NT, true>, k_block_fwd_mma<CP, HP, NT, false> }
 const MVariant kMV[] = {
     STG_MV(8, 8, 2),   STG_MV(8, 8, 4),   STG_MV(8, 8, 8),
     STG_MV(16, 8, 2),  STG_MV(16, 8, 4),  STG_MV(16, 8, 6),  STG_MV(16, 8, 8),
@@ -920,7 +502,6 @@ void set_mattrs() {
   for (int i = 0; i < kNMV; ++i) {
     cudaFuncSetAttribute(kMV[i].fwd_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCapM);
     cudaFuncSetAttribute(kMV[i].fwd_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCapM);
-    cudaFuncSetAttribute(kMV[i].bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCapM);
   }
   g_mattr[dev] = true;
 }
@@ -935,7 +516,7 @@ int rows_of_fwd(const BlkArgs& a) {
   }
   return rm;
 }
-int rows_of_bwd(const BlkArgs& a) { return bwd_rows_exact(a); }
+
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   if (!e) return dflt;
@@ -980,41 +561,6 @@ bool plan_blocks_mma_fwd(BlkArgs& a, BlkPlan& p) {
   return false;
 }
 
-bool plan_blocks_mma_bwd(BlkArgs& a, BlkPlan& p) {
-  int Hmax = 0, Mmax = 0;
-  for (int z = 0; z < a.nblk; ++z) {
-    Hmax = a.b[z].H > Hmax ? a.b[z].H : Hmax;
-    Mmax = a.b[z].w * a.N > Mmax ? a.b[z].w * a.N : Mmax;
-  }
-  const MVariant* v = pick_mv(a.C, Hmax, Mmax);
-  if (!v || (a.C & 1) || ((uintptr_t)a.x & 7)) return false;
-  if (p.mma_f && (v->CP != p.CP || v->HP != p.HP)) return false;
-  const int nwarps = env_int("STG_BWD_WARPS", v->NT <= 4 ? 8 : 4);
-  int saved[2] = {a.b[0].nchunk_b, a.b[1].nchunk_b};
-  // time steps per chunk so that the windows touching it are one per warp
-  for (int wp = env_int("STG_BWD_WP", nwarps); wp >= 1; --wp) {
-    int gx = 0;
-    for (int z = 0; z < a.nblk; ++z) {
-      BlkDev& k = a.b[z];
-      int per = wp * k.stride - (k.w - 1);
-      if (per < k.stride) per = k.stride;
-      per = (per / k.stride) * k.stride;
-      k.nchunk_b = (a.T + per - 1) / per;
-      gx = k.nchunk_b > gx ? k.nchunk_b : gx;
-    }
-    const int rows_max = rows_of_bwd(a);
-    const MLay l = make_mlay(v->CP, v->HP, v->NT * 8, Mmax, a.C, rows_max, nwarps, 2);
-    const size_t sm = 16 + (size_t)l.total * 4;
-    if (sm <= kSmemCapM) {
-      p.mma_b = 1; p.CP = v->CP; p.HP = v->HP; p.NT = v->NT;
-      p.smem_b = sm; p.grid_x_b = gx; p.threads_b = nwarps * 32;
-      return true;
-    }
-  }
-  a.b[0].nchunk_b = saved[0]; a.b[1].nchunk_b = saved[1];      // keep the SIMT plan intact
-  return false;
-}
-
 int launch_block_forward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   set_mattrs();
   const MVariant* v = find_mv(p.CP, p.HP, p.NT);
@@ -1024,16 +570,6 @@ int launch_block_forward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s)
   ProfScope ps(kProfFwdMain, s);
   if (a.training) v->fwd_train<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max);
   else v->fwd_eval<<<grid, p.threads_f, p.smem_f, s>>>(a, rows_max);
-  return cudaGetLastError() == cudaSuccess ? 0 : -3;
-}
-
-int launch_block_backward_mma(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
-  set_mattrs();
-  const MVariant* v = find_mv(p.CP, p.HP, p.NT);
-  if (!v) return -2;
-  const int rows_max = rows_of_bwd(a);
-  ProfScope ps(kProfBwdMain, s);
-  v->bwd<<<dim3(p.grid_x_b, a.B, a.nblk), p.threads_b, p.smem_b, s>>>(a, rows_max);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
