@@ -52,9 +52,10 @@ def load_golden(path, dtype=torch.float32):
 OUT_TOL = 2e-5            # outputs: every forward product is fp32-accurate (3-term TF32 split on the tcgen05 path)
 GRAD_TOL_FP32 = 3e-4      # gradients, fp32 SIMT paths: relative to the tensor's own largest entry (summation-order noise
                           # of float atomics over ~1e5-row reductions: measured up to 1.7e-4 on FD003, B=70)
-GRAD_TOL_TC = 3e-3        # gradients through the single-pass TF32 backward products of the tcgen05 path: operand
+GRAD_TOL_TC = 5e-3        # gradients through the single-pass TF32 backward products of the tcgen05 path: operand
                           # rounding 2^-12 per factor, three products deep, and reductions over ~1e5 rows that cancel
-                          # (BatchNorm shifts, biases).  Measured per tensor: 1e-4 .. 8e-4 typical, 1.8e-3 worst
+                          # (BatchNorm shifts, biases).  Measured per tensor: 1e-4 .. 8e-4 typical, 2.7e-3 worst (a bias gradient that
+                          # is the sum of 9e4 rows cancelling to ~1 % of their size)
                           # (scripts/tc_parity.py, scripts/tc_parity_model.py; profiles/r02_tc_parity.md)
 
 
