@@ -420,11 +420,13 @@ def run_native(args):
             ms = float(t)
         return ms
 
-    for i in range(args.warmup):
-        step_resident(i)
-    for i in range(max(3, args.warmup // 2)):
-        step_e2e(i)
+    # the sampler thread starts with the warm-up (NVML initialisation takes longer than a short timed region): every
+    # sample is taken while this rank's GPU runs the step
     with ClockSampler(local) as clk:
+        for i in range(args.warmup):
+            step_resident(i)
+        for i in range(max(3, args.warmup // 2)):
+            step_e2e(i)
         ms_res = timed(step_resident, args.steps)
         ms_e2e = timed(step_e2e, args.steps)
     # second pass: same steps with per-kernel events of our library (roofline of the dominant kernel)
