@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(256) k_xmoments_prep(const BlkArgs a, int CP, 
 // l + 16 are folded with one shuffle and every warp issues 32 double atomics in all.  grid (ceil(T * wpt / 8)), 256.
 __global__ void __launch_bounds__(256) k_xmoments_prep16(const BlkArgs a, int CP, int HP, double* xmom,
                                                          unsigned* counter, int nslice) {
+  pdl_sync();
   __shared__ PrepScratch ps;
   __shared__ float red[8][32];
   __shared__ int s_last;
@@ -1276,7 +1277,7 @@ int launch_xmoments_prep(const BlkArgs& a, const BlkPlan& p, double* xmom, unsig
     int nslice = (148 * 4 + a.T - 1) / a.T;
     if (nslice * 8 > a.B) nslice = (a.B + 7) / 8;
     if (nslice < 1) nslice = 1;
-    k_xmoments_prep16<<<a.T * nslice, 256, 0, s>>>(a, p.CP, p.HP, xmom, counter, nslice);
+    launch_pdl(k_xmoments_prep16, dim3(a.T * nslice), dim3(256), 0, s, a, p.CP, p.HP, xmom, counter, nslice);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
   }
   k_xmoments_prep<<<dim3(a.T, nb), 256, 0, s>>>(a, p.CP, p.HP, xmom, counter);

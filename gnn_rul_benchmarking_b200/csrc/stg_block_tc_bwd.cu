@@ -7,12 +7,12 @@ namespace stg {
 namespace tc {
 
 template <int WR, int NT, bool SPLIT>
-__global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int ncta0) {
+__global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int ncta0, int pf) {
   constexpr int WPT = 128 / WR;
   extern __shared__ unsigned char smraw[];
   __shared__ TcCtl ctl;
   unsigned char* sm = reinterpret_cast<unsigned char*>(((uintptr_t)smraw + 1023) & ~(uintptr_t)1023);
-  const SmemLayout L = make_layout(WR, true, SPLIT);
+  const SmemLayout L = make_layout(WR, true, SPLIT, pf ? 2 * (NT ? NT : a.N) : 0);
   const int z = (int)blockIdx.x < ncta0 ? 0 : 1;
   const BlkDev& k = a.b[z];
   const int cta = z == 0 ? blockIdx.x : blockIdx.x - ncta0;
@@ -34,13 +34,35 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   const long long nwin = (long long)a.B * Lw;
   const int ntiles = (int)((nwin + WPT - 1) / WPT);
 
-  if (tid == 0) mbar_init(&ctl.bar, 1);
+  // saved forward tensors of the block; with pf != 0 the F|V and softmax blocks of a tile's WPT windows (one contiguous
+  // run each) are staged in shared memory by two TMA bulk copies issued one tile ahead
+  const int MP = saved_mp(M);
+  const float* fvs = k.yp + saved_off_fv(nwin * M, H);
+  const float* ps = k.yp + saved_off_p(nwin * M, H);
+  const float* pf_fv = reinterpret_cast<const float*>(sm + L.pf_fv);
+  const float* pf_p = reinterpret_cast<const float*>(sm + L.pf_p);
+  auto issue_pf = [&](int t) {
+    const uint32_t bfv = (uint32_t)(WPT * kCPH * M * 4), bp = (uint32_t)(WPT * MP * M * 4);
+    mbar_expect_tx(&ctl.bar_pf, bfv + bp);
+    tma_bulk_g2s(sm + L.pf_fv, fvs + (size_t)t * (WPT * kCPH * M), bfv, &ctl.bar_pf);
+    tma_bulk_g2s(sm + L.pf_p, ps + (size_t)t * (WPT * MP * M), bp, &ctl.bar_pf);
+  };
+  if (tid == 0) {
+    mbar_init(&ctl.bar, 1);
+    mbar_init(&ctl.bar_pf, 1);
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl.tmem_base)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  tc_prologue(a, k, sm, L, SPLIT, true);
   float* cst = reinterpret_cast<float*>(sm + L.cst);
+  float* red = cst + kCstRed;         // G[24][17] (column 16 = column sums of [dF | dV]) then dbt[8]
+  // operand buffers whose pad parts are read by the tensor core but never written per tile
+  for (int idx = tid; idx < (L.pf_fv - L.ra) / 16; idx += 128) reinterpret_cast<float4*>(sm + L.ra)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int idx = tid; idx < 24 * 17 + 8; idx += 128) red[idx] = 0.f;
+  pdl_sync();
+  if (tid == 0 && pf && cta < ntiles && (long long)(cta + 1) * WPT <= nwin) issue_pf(cta);
+  tc_prologue(a, k, sm, L, SPLIT, true);
   // BN1 backward coefficients: [0]=a1 [1]=c1 [2]=mu1 [3]=r1 [4]=g1*r1 [5]=q1 [6]=q2
   if (tid < 8) {
     float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -63,10 +85,6 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
 #pragma unroll
     for (int q = 0; q < 7; ++q) cst[kCstBn1 + q * 8 + tid] = v[q];
   }
-  // operand buffers whose pad parts are read by the tensor core but never written per tile
-  for (int idx = tid; idx < (L.wc2 - L.ra) / 16; idx += 128) reinterpret_cast<float4*>(sm + L.ra)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float* red = cst + kCstRed;         // G[24][17] (column 16 = column sums of [dF | dV]) then dbt[8]
-  for (int idx = tid; idx < 24 * 17 + 8; idx += 128) red[idx] = 0.f;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -74,7 +92,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   const uint32_t tmem = ctl.tmem_base;
   const uint32_t lane_t = tmem + ((uint32_t)(warp * 32) << 16);
   constexpr uint32_t regA = 0, regB = 128;
-  const uint32_t t2l_lo = dlo(smem_u32(sm + L.t2) + 16 * 1024, 2048),
+  const uint32_t t2l_lo = dlo(smem_u32(sm + L.t2) + 12 * 1024, 2048),
                  yk_lo = dlo(smem_u32(sm + L.yk), 2048), ra_lo = dlo(smem_u32(sm + L.ra), 512),
                  rb_lo = dlo(smem_u32(sm + L.rb), 512), t1_lo = dlo(smem_u32(sm + L.t1), WR * 128),
                  t2_lo = dlo(smem_u32(sm + L.t2), WR * 128), t1g_lo = dlo(smem_u32(sm + L.t1), 512),
@@ -86,7 +104,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   unsigned char* t1 = sm + L.t1;
   unsigned char* t2 = sm + L.t2;
   float4* t2k4 = reinterpret_cast<float4*>(t2);       // [dF | dV] rows, K-major, for the dx projection ...
-  float4* t2l4 = reinterpret_cast<float4*>(t2 + 16 * 1024);      // ... and their tf32 residuals
+  float4* t2l4 = reinterpret_cast<float4*>(t2 + 12 * 1024);      // ... and their tf32 residuals
 
   const int wl = tid / WR, i = tid - wl * WR;
   const bool row_ok = i < M;
@@ -103,17 +121,15 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   for (int c = 0; c < kCP; ++c) sof[c] = 0.f;
 #pragma unroll
   for (int h = 0; h < kHP; ++h) sov[h] = dbt_acc[h] = 0.f;
-  uint32_t ph = 0;
-
-  const int MP = saved_mp(M);
-  const float* fvs = k.yp + saved_off_fv(nwin * M, H);
-  const float* ps = k.yp + saved_off_p(nwin * M, H);
+  uint32_t ph = 0, ph_pf = 0;
 
   for (int tile = cta; tile < ntiles; tile += ncta) {
     const long long g = (long long)tile * WPT + wl;
     const bool valid = row_ok && g < nwin;
     const size_t grow = (size_t)g * M + i;          // row of this thread in the [B*L*M, .] saved tensors
+    const bool staged = pf && (long long)(tile + 1) * WPT <= nwin;      // partial last tile: plain loads
     STG_STAMP(0)
+    if (staged) { mbar_wait(&ctl.bar_pf, ph_pf); ph_pf ^= 1; }
     // ---- step 1: this row's x, saved F | V, saved softmax row, Y', dout -> dY'; operands of dA = dY' . V^T
     float dY[8];
     float es[WR];                                   // softmax numerators e_k of the row (sign bit: S > 0)
@@ -123,14 +139,25 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
       if (valid) {
         const int b = (int)(g / Lw), l = (int)(g - (long long)b * Lw);
         load_row<16>(a.x + (((size_t)b * T + (size_t)l * s) * N + i) * C, C, xvec, xr);
-        const float* fsrc = fvs + (size_t)g * kCPH * M + i;
+        if (staged) {
+          const float* fsrc = pf_fv + wl * kCPH * M + i;
 #pragma unroll
-        for (int c = 0; c < kCPH; ++c) fv[c] = __ldg(fsrc + c * M);
-        const float* psrc = ps + (size_t)g * MP * M + i;
+          for (int c = 0; c < kCPH; ++c) fv[c] = fsrc[c * M];
+          const float* psrc = pf_p + wl * MP * M + i;
 #pragma unroll
-        for (int kk = 0; kk < WR; ++kk)
-          if (kk < M) es[kk] = __ldg(psrc + kk * M);
-        inv = __ldg(psrc + (size_t)M * M);
+          for (int kk = 0; kk < WR; ++kk)
+            if (kk < M) es[kk] = psrc[kk * M];
+          inv = psrc[M * M];
+        } else {
+          const float* fsrc = fvs + (size_t)g * kCPH * M + i;
+#pragma unroll
+          for (int c = 0; c < kCPH; ++c) fv[c] = __ldg(fsrc + c * M);
+          const float* psrc = ps + (size_t)g * MP * M + i;
+#pragma unroll
+          for (int kk = 0; kk < WR; ++kk)
+            if (kk < M) es[kk] = __ldg(psrc + kk * M);
+          inv = __ldg(psrc + (size_t)M * M);
+        }
         load_row<8>(k.yp + grow * H, H, yvec, yv);
         const float* dr = k.dout + (size_t)b * k.dout_bs + ((size_t)l * N + n_i) * H;
         load_row<8>(dr, H, yvec && (((uintptr_t)dr & 15) == 0), dv);
@@ -178,6 +205,9 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
       // dA = dY' . V^T   (K = 8: one instruction)
       mma_ss(tmem + regB, dsc(yk_lo, kHiK), dsc(yk_lo + 256, kHiK), id, 0);
       mma_commit(&ctl.bar);
+      // every thread is past its reads of the staged blocks: fetch the next tile's
+      const int nt = tile + ncta;
+      if (pf && nt < ntiles && (long long)(nt + 1) * WPT <= nwin) issue_pf(nt);
     }
     STG_STAMP(3)
     mbar_wait(&ctl.bar, ph); ph ^= 1;
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
 }
 
 template <int WR, int NT, bool SPLIT>
-static void launch_bwd(const BlkArgs& a, int total, int n0, size_t smem, cudaStream_t s) {
+static void launch_bwd(const BlkArgs& a, int total, int n0, size_t smem, int pf, cudaStream_t s) {
   static bool attr[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -408,7 +438,7 @@ static void launch_bwd(const BlkArgs& a, int total, int n0, size_t smem, cudaStr
     cudaFuncSetAttribute(k_block_bwd_tc<WR, NT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr[dev] = true;
   }
-  k_block_bwd_tc<WR, NT, SPLIT><<<total, 128, smem, s>>>(a, n0);
+  launch_pdl(k_block_bwd_tc<WR, NT, SPLIT>, dim3(total), dim3(128), smem, s, a, n0, pf);
 }
 
 }  // namespace tc
@@ -424,15 +454,25 @@ extern "C" int stg_debug_tc_stamps_bwd(long long* out32) {
 
 int launch_block_backward_tc(const BlkArgs& a, const BlkPlan& p, cudaStream_t s) {
   using namespace tc;
-  const SmemLayout L = make_layout(p.tc_wr, true, p.tc_split != 0);
+  // 227 KB usable per SM, 1 KB reserved per CTA.  The saved blocks are staged by TMA one tile ahead when that keeps the
+  // CTAs per SM of the plain-load variant (STG_TC_NO_PREFETCH=1 forces plain loads).
+  auto fit = [](const SmemLayout& l) { return 2 * ((size_t)l.total + 1024) <= 227 * 1024 ? 2 : 1; };
+  static const bool no_pf = [] { const char* e = getenv("STG_TC_NO_PREFETCH"); return e && *e == '1'; }();
+  SmemLayout L = make_layout(p.tc_wr, true, p.tc_split != 0);
+  int pf = 0;
+  {
+    const SmemLayout Lp = make_layout(p.tc_wr, true, p.tc_split != 0, 2 * a.N);
+    const bool aligned = (((uintptr_t)a.b[0].yp | (uintptr_t)a.b[1].yp) & 15) == 0;
+    if (!no_pf && aligned && fit(Lp) == fit(L)) { L = Lp; pf = 1; }
+  }
   int n0 = 0, total = 0;
-  const int per_sm = 2 * ((size_t)L.total + 1024) <= 227 * 1024 ? 2 : 1;      // 227 KB usable per SM, 1 KB reserved per CTA
+  const int per_sm = fit(L);
   split_ctas(a, p.tc_wr, per_sm * sm_count(), &n0, &total);
   ProfScope ps(kProfBwdMain, s);
 #define STG_TC_BWD(WR, NT)                                                  \
   do {                                                                      \
-    if (p.tc_split) launch_bwd<WR, NT, true>(a, total, n0, L.total, s);     \
-    else launch_bwd<WR, NT, false>(a, total, n0, L.total, s);               \
+    if (p.tc_split) launch_bwd<WR, NT, true>(a, total, n0, L.total, pf, s);     \
+    else launch_bwd<WR, NT, false>(a, total, n0, L.total, pf, s);               \
   } while (0)
   if (p.tc_wr == 32) {
     if (a.N == 14) STG_TC_BWD(32, 14); else STG_TC_BWD(32, 0);

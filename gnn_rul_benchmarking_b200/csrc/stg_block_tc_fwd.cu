@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(128, WR == 32 ? 4 : 2) k_block_fwd_tc(const Bl
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl.tmem_base)), "r"(128));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  pdl_sync();
   tc_prologue(a, k, sm, L, SPLIT, false);
   float* cst = reinterpret_cast<float*>(sm + L.cst);
   if (!TRAIN && tid < 8) {
@@ -314,8 +315,8 @@ static void launch_fwd(const BlkArgs& a, int total, int n0, size_t smem, cudaStr
     cudaFuncSetAttribute(k_block_fwd_tc<WR, NT, false, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr[dev] = true;
   }
-  if (a.training) k_block_fwd_tc<WR, NT, true, SPLIT><<<total, 128, smem, s>>>(a, n0);
-  else k_block_fwd_tc<WR, NT, false, SPLIT><<<total, 128, smem, s>>>(a, n0);
+  if (a.training) launch_pdl(k_block_fwd_tc<WR, NT, true, SPLIT>, dim3(total), dim3(128), smem, s, a, n0);
+  else launch_pdl(k_block_fwd_tc<WR, NT, false, SPLIT>, dim3(total), dim3(128), smem, s, a, n0);
 }
 
 }  // namespace tc

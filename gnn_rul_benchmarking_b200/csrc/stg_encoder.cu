@@ -103,19 +103,6 @@ inline int tile_rows_for(const EncArgs& a, int ph) {
   return 0;
 }
 
-STG_DEVINL float keep_scale(const EncArgs& a, size_t idx) {
-  if (!a.training || a.pdrop <= 0.f) return 1.f;
-  const float sc = 1.f / (1.f - a.pdrop);
-  if (a.keep) return a.keep[idx] * sc;
-  unsigned long long z = a.seed + (a.seed_ptr ? (unsigned long long)*a.seed_ptr * 0xD1B54A32D192ED03ull : 0ull) +
-                         (unsigned long long)idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = (float)(z >> 40) * (1.f / 16777216.f);
-  return u >= a.pdrop ? sc : 0.f;
-}
-
 // BN forward coefficients of one layer into smem: A = g*r, Cc = beta - A*mu, mu, r.
 // Threads [0,n).  stats: sums / sums of squares (training) or nullptr (running statistics).
 STG_DEVINL void bn_coefs(float* dst, int n, const double* stats, double count, const float* g, const float* be,
@@ -408,7 +395,7 @@ __global__ void __launch_bounds__(kThreads) k_encoder(const EncArgs a) {
         const int rr = o / C, c = o - rr * C;
         const float hn = fmaf(A3[c], zz[c * TRP + rr], C3[c]) + pe[rowt[rr] * C + c];
         // reference dropout layout [B*N,T,C]
-        a.h[(size_t)(r0 + rr) * C + c] = hn * keep_scale(a, (size_t)rowk[rr] * C + c);
+        a.h[(size_t)(r0 + rr) * C + c] = hn * drop_scale(a, drop_row_key(a, (size_t)rowk[rr]), (size_t)rowk[rr], C, c);
       }
       continue;
     }
@@ -417,7 +404,7 @@ __global__ void __launch_bounds__(kThreads) k_encoder(const EncArgs a) {
         // ---- dhn = dropout'(dh) ----
         for (int o = tid; o < C * TR; o += kThreads) {
           const int rr = o / C, c = o - rr * C;
-          z2[c * TRP + rr] = rr < rows ? a.dh[(size_t)(r0 + rr) * C + c] * keep_scale(a, (size_t)rowk[rr] * C + c) : 0.f;
+          z2[c * TRP + rr] = rr < rows ? a.dh[(size_t)(r0 + rr) * C + c] * drop_scale(a, drop_row_key(a, (size_t)rowk[rr]), (size_t)rowk[rr], C, c) : 0.f;
         }
         __syncthreads();
         if (PH == 4) {

@@ -14,8 +14,9 @@
 namespace stg {
 namespace {
 
-constexpr int kT = 256;          // threads per CTA == rows per tile
-constexpr int kTP = 260;         // smem row pitch of the staged columns (float4-aligned)
+constexpr int kT = 128;          // threads per CTA == rows per CTA tile
+constexpr int kLP = 256;         // rows per workspace tile ([tile][feature][256]): a CTA tile is one half of it
+constexpr int kTP = 132;         // smem row pitch of the staged columns (float4-aligned)
 
 template <int P_, int K_, int EH_, int E_, int C_>
 struct EncDims {
@@ -23,19 +24,6 @@ struct EncDims {
   static constexpr int pad1 = K / 2, L1 = P + 2 * pad1 - K + 1, L2 = L1 + 2 - K + 1;
   static constexpr int EL2 = E * L2, NL1 = EH * L1;
 };
-
-STG_DEVINL float keep_scale_f(const EncArgs& a, size_t idx) {
-  if (!a.training || a.pdrop <= 0.f) return 1.f;
-  const float sc = 1.f / (1.f - a.pdrop);
-  if (a.keep) return a.keep[idx] * sc;
-  unsigned long long z = a.seed + (a.seed_ptr ? (unsigned long long)*a.seed_ptr * 0xD1B54A32D192ED03ull : 0ull) +
-                         (unsigned long long)idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = (float)(z >> 40) * (1.f / 16777216.f);
-  return u >= a.pdrop ? sc : 0.f;
-}
 
 STG_DEVINL void bn_coefs_f(float* dst, int n, const double* stats, double count, const float* g, const float* be,
                            float* rm, float* rv, float eps, float momentum, bool update) {
@@ -63,11 +51,43 @@ STG_DEVINL void bn_coefs_f(float* dst, int n, const double* stats, double count,
   }
 }
 
-// per-warp partial sums in registers' place: swarp[warp][idx] accumulates this warp's tiles (one owner
-// lane per slot, no atomics); the CTA reduces the 8 warps in double at the very end
-STG_DEVINL void stat_add_f(float (*swarp)[2 * 48], int idx, float v) {
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) swarp[threadIdx.x >> 5][idx] += v;
+// Warp totals of NP (power of two, <= 32) per-thread values with a halving butterfly: every exchange step halves the
+// number of live values (NP - 1 shuffles for NP = 32 instead of 5 NP for one warp_sum per value).  Afterwards lane l
+// holds the total of value l / (32 / NP).
+template <int NP>
+STG_DEVINL float warp_multi_sum(float (&w)[NP]) {
+  const int lane = threadIdx.x & 31;
+  int o = 16;
+#pragma unroll
+  for (int n = NP; n > 1; n >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? w[i] : w[i + n / 2];
+      const float keep = up ? w[i + n / 2] : w[i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float r = w[0];
+#pragma unroll
+  for (; o >= 1; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+
+// swarp[warp][idx] accumulates this warp's tiles (one owner lane per slot, no atomics); the CTA reduces its warps in
+// double at the very end.  v[0..NS) are this thread's contributions to slots 0..NS-1.
+template <int NS, int BASE = 0>
+STG_DEVINL void stat_flush(float (*swarp)[2 * 48], const float (&v)[NS]) {
+  constexpr int n = NS - BASE < 32 ? NS - BASE : 32;          // values of this chunk
+  constexpr int NP = n > 16 ? 32 : n > 8 ? 16 : 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float w[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) w[i] = i < n ? v[i < n ? BASE + i : 0] : 0.f;
+  const float r = warp_multi_sum<NP>(w);
+  constexpr int per = 32 / NP;                                 // lanes holding the same total
+  if ((lane & (per - 1)) == 0 && lane / per < n) swarp[warp][BASE + lane / per] += r;
+  if constexpr (BASE + 32 < NS) stat_flush<NS, BASE + 32>(swarp, v);
 }
 
 template <class D>
@@ -159,11 +179,30 @@ STG_DEVINL void store_row(float* __restrict__ p, const float (&v)[C]) {
   }
 }
 
+#ifdef STG_ENC_TIMING
+// debug build only (scripts/enc_cta_times.py): per phase and CTA, globaltimer at entry and clock64 deltas of the
+// prologue / tile loop / epilogue
+__device__ unsigned long long g_enc_time[9][1024][8];
+#define ENC_STAMP(slot)                                                                        \
+  if (threadIdx.x == 0 && blockIdx.x < 1024) {                                                 \
+    if (slot == 0) {                                                                           \
+      unsigned long long tg;                                                                   \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg));                                   \
+      g_enc_time[PH][blockIdx.x][0] = tg;                                                      \
+      enc_t0 = clock64();                                                                      \
+    } else {                                                                                   \
+      g_enc_time[PH][blockIdx.x][slot] = (unsigned long long)(clock64() - enc_t0);             \
+    }                                                                                          \
+  }
+#else
+#define ENC_STAMP(slot)
+#endif
+
 STG_DEVINL float dot4(const float4 a, const float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 STG_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 template <class D, int PH>
-__global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs a) {
+__global__ void __launch_bounds__(kT, PH == 8 ? 1 : (D::C > 16 || D::E > 6) ? 3 : 5) k_enc_fast(const EncArgs a) {
   constexpr int P = D::P, K = D::K, EH = D::EH, E = D::E, C = D::C, L1 = D::L1, L2 = D::L2, EL2 = D::EL2, NL1 = D::NL1;
   constexpr int MAXCH = EH > E ? (EH > C ? EH : C) : (E > C ? E : C);
   constexpr int NPAIR = PH == 5 ? C * EL2 + C : PH == 6 ? E * EH * K : PH == 7 ? EH * K : 1;
@@ -178,6 +217,10 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
   extern __shared__ __align__(16) float stage[];      // [features][kTP] columns for the pair reductions / pe
   const int tid = threadIdx.x;
   const int N = a.N, T = a.T;
+#ifdef STG_ENC_TIMING
+  long long enc_t0 = 0;
+#endif
+  ENC_STAMP(0)
 
   const double cnt1 = (double)a.R * L1, cnt2 = (double)a.R * L2, cnt3 = (double)a.R;
   const double* S1 = a.st;
@@ -187,6 +230,10 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
   double* Bq2 = Bq3 + 2 * C;
   double* Bq1 = Bq2 + 2 * E;
 
+  for (int i = tid; i < NPAIR; i += kT) accW[i] = 0.f;
+  static_assert(MAXCH <= 48, "stat slots");
+  for (int i = tid; i < (kT / 32) * 2 * 48; i += kT) (&sacc[0][0])[i] = 0.f;
+  pdl_sync();
   for (int i = tid; i < EH * K; i += kT) W1[i] = a.W1[i];
   for (int i = tid; i < E * EH * K; i += kT) W2[i] = a.W2[i];
   for (int i = tid; i < C * EL2; i += kT) W3[i] = a.W3[i];
@@ -195,6 +242,7 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
   if (PH >= 1) bn_coefs_f(cf1, EH, tr ? S1 : nullptr, cnt1, a.g1, a.be1, a.rm1, a.rv1, a.eps, a.momentum, tr && first && PH == 1);
   if (PH >= 2) bn_coefs_f(cf2, E, tr ? S2 : nullptr, cnt2, a.g2, a.be2, a.rm2, a.rv2, a.eps, a.momentum, tr && first && PH == 2);
   if (PH >= 3) bn_coefs_f(cf3, C, tr ? S3 : nullptr, cnt3, a.g3, a.be3, a.rm3, a.rv3, a.eps, a.momentum, tr && first && PH == 3);
+  ENC_STAMP(7)
   if (PH == 3 || PH == 8) for (int i = tid; i < T * C; i += kT) stage[i] = a.pe[i];
   if (PH >= 5 && PH <= 7) for (int c = tid; c < C; c += kT) {
     q3[c] = (float)(Bq3[c] / cnt3);
@@ -242,11 +290,9 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
         }
     }
   }
-  for (int i = tid; i < NPAIR; i += kT) accW[i] = 0.f;
-  static_assert(MAXCH <= 48, "stat slots");
-  for (int i = tid; i < (kT / 32) * 2 * 48; i += kT) (&sacc[0][0])[i] = 0.f;
   __syncthreads();
 
+  ENC_STAMP(1)
   const float *A1 = cf1, *C1 = cf1 + EH, *mu1 = cf1 + 2 * EH, *r1 = cf1 + 3 * EH;
   const float *A2 = cf2, *C2 = cf2 + E, *mu2 = cf2 + 2 * E, *r2 = cf2 + 3 * E;
   const float *A3 = cf3, *C3 = cf3 + C, *mu3 = cf3 + 2 * C, *r3 = cf3 + 3 * C;
@@ -265,10 +311,12 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
       t = bt % T;
       b = bt / T;
     }
-    float* c2t = a.c2raw + (size_t)tile * EL2 * kT + tid;     // + k*kT
-    float* z3t = a.z3raw + (size_t)tile * C * kT + tid;       // + c*kT
-    float* dn2t = a.dn2 + (size_t)tile * EL2 * kT + tid;
-    float* dn1t = a.dn1 + (size_t)tile * NL1 * kT + tid;
+    const size_t wt = (size_t)(tile >> 1);                    // workspace tile, this CTA tile's half of its rows
+    const int wo = (tile & 1) * kT + tid;
+    float* __restrict__ c2t = a.c2raw + wt * EL2 * kLP + wo;      // + k*kLP
+    float* __restrict__ z3t = a.z3raw + wt * C * kLP + wo;        // + c*kLP
+    float* __restrict__ dn2t = a.dn2 + wt * EL2 * kLP + wo;
+    float* __restrict__ dn1t = a.dn1 + wt * NL1 * kLP + wo;
 
     // ---- x and conv1 where the phase needs them ----
     float x[P], c1[NL1];
@@ -285,6 +333,7 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
     }
 
     if constexpr (PH == 0) {
+      float st[2 * EH];
 #pragma unroll
       for (int ch = 0; ch < EH; ++ch) {
         float s = 0.f, ss = 0.f;
@@ -294,16 +343,18 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
           s += v;
           ss = fmaf(v, v, ss);
         }
-        stat_add_f(sacc, ch, s);
-        stat_add_f(sacc, EH + ch, ss);
+        st[ch] = s;
+        st[EH + ch] = ss;
       }
+      stat_flush<2 * EH>(sacc, st);
     } else if constexpr (PH == 1) {
       float a1[NL1], c2[EL2];
 #pragma unroll
       for (int i = 0; i < NL1; ++i) a1[i] = fmaxf(fmaf(A1[i / L1], c1[i], C1[i / L1]), 0.f);
       conv2_row<D>(W2, a1, c2);
 #pragma unroll
-      for (int k = 0; k < EL2; ++k) c2t[k * kT] = c2[k];
+      for (int k = 0; k < EL2; ++k) c2t[k * kLP] = c2[k];
+      float st[2 * E];
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         float s = 0.f, ss = 0.f;
@@ -313,16 +364,20 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
           s += v;
           ss = fmaf(v, v, ss);
         }
-        stat_add_f(sacc, e, s);
-        stat_add_f(sacc, E + e, ss);
+        st[e] = s;
+        st[E + e] = ss;
       }
+      stat_flush<2 * E>(sacc, st);
     } else if constexpr (PH == 2 || PH == 3 || PH == 8) {
       float z[C];
       if constexpr (PH == 2 || PH == 8) {
         float a2[EL2];
         if constexpr (PH == 2) {
+          // all loads of the row first (one round trip), then the arithmetic
 #pragma unroll
-          for (int k = 0; k < EL2; ++k) a2[k] = fmaxf(fmaf(A2[k / L2], c2t[k * kT], C2[k / L2]), 0.f);
+          for (int k = 0; k < EL2; ++k) a2[k] = act ? c2t[k * kLP] : 0.f;
+#pragma unroll
+          for (int k = 0; k < EL2; ++k) a2[k] = fmaxf(fmaf(A2[k / L2], a2[k], C2[k / L2]), 0.f);
         } else {                 // eval forward: whole chain in one pass (no stored intermediates)
           float a1[NL1], c2[EL2];
 #pragma unroll
@@ -340,58 +395,92 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < C; ++c) z[c] = z3t[c * kT];
+        for (int c = 0; c < C; ++c) z[c] = act ? z3t[c * kLP] : 0.f;
       }
       if constexpr (PH == 2) {
 #pragma unroll
+        for (int c = 0; c < C; ++c) z3t[c * kLP] = z[c];
+        float st[2 * C];
+#pragma unroll
         for (int c = 0; c < C; ++c) {
-          z3t[c * kT] = z[c];
           const float v = act ? z[c] : 0.f;
-          stat_add_f(sacc, c, v);
-          stat_add_f(sacc, C + c, v * v);
+          st[c] = v;
+          st[C + c] = v * v;
         }
+        stat_flush<2 * C>(sacc, st);
       } else if (act) {
         float* hr = a.h + (size_t)r * C;
-        const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
+        const size_t krow = (size_t)(b * N + n) * T + t;
+      const unsigned long long dkey = drop_row_key(a, krow);
         const float* pe = stage + t * C;
         float hv[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) hv[c] = (fmaf(A3[c], z[c], C3[c]) + pe[c]) * keep_scale_f(a, kbase + c);
+        for (int c = 0; c < C; ++c) hv[c] = (fmaf(A3[c], z[c], C3[c]) + pe[c]) * drop_scale(a, dkey, krow, C, c);
         store_row<C>(hr, hv);
       }
     } else if constexpr (PH == 4) {
-      const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
-      float dhv[C];
+      const size_t krow = (size_t)(b * N + n) * T + t;
+      const unsigned long long dkey = drop_row_key(a, krow);
+      float dhv[C], z3[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) z3[c] = act ? z3t[c * kLP] : 0.f;
       if (act) {
         if (a.fin.nblk) {
           float xv[C];
           load_row<C>(a.h + (size_t)r * C, xv);
 #pragma unroll
           for (int c = 0; c < C; ++c) dhv[c] = 0.f;
-          for (int z = 0; z < a.fin.nblk; ++z) {
-            const float* tb = stage + z * (4 * C + T);
-            const float cn = tb[4 * C + t];
-            float dv[C];
-            if (a.fin.unfolded) {
-              // sum the windows covering time step t (rows (l, j, n) with l*stride + j == t)
+          if (C <= 16 && a.fin.unfolded && a.fin.nblk == 2 && a.fin.w[0] == 2 && a.fin.w[1] == 2) {
+            // the usual shape (two blocks, windows of two time steps): the (up to) four partial rows covering
+            // time step t are fetched together, rows (l, j, n) with l*stride + j == t
+            float pv[4][C];
 #pragma unroll
-              for (int c = 0; c < C; ++c) dv[c] = 0.f;
-              const int Lz = a.fin.L[z], sz = a.fin.stride[z], wz = a.fin.w[z];
-              for (int j = 0; j < wz; ++j) {
-                const int d = t - j;
-                if (d < 0 || d % sz || d / sz >= Lz) continue;
-                float pv[C];
-                load_row<C>(a.fin.dxp[z] + ((((size_t)b * Lz + d / sz) * wz + j) * N + n) * C, pv);
+            for (int q = 0; q < 4; ++q) {
+              const int z = q >> 1, j = q & 1;
+              const int Lz = a.fin.L[z], sz = a.fin.stride[z];
+              const int d = t - j, l = d / sz;
+              const bool ok = d >= 0 && l * sz == d && l < Lz;
+              if (ok) load_row<C>(a.fin.dxp[z] + ((((size_t)b * Lz + l) * 2 + j) * N + n) * C, pv[q]);
+              else {
 #pragma unroll
-                for (int c = 0; c < C; ++c) dv[c] += pv[c];
+                for (int c = 0; c < C; ++c) pv[q][c] = 0.f;
               }
-            } else {
-              load_row<C>(a.fin.dxp[z] + (size_t)r * C, dv);
             }
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              const float xh = (xv[c] - tb[c]) * tb[C + c];
-              dhv[c] += dv[c] - cn * (tb[2 * C + c] + xh * tb[3 * C + c]);
+            for (int z = 0; z < 2; ++z) {
+              const float* tb = stage + z * (4 * C + T);
+              const float cn = tb[4 * C + t];
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const float xh = (xv[c] - tb[c]) * tb[C + c];
+                dhv[c] += (pv[2 * z][c] + pv[2 * z + 1][c]) - cn * (tb[2 * C + c] + xh * tb[3 * C + c]);
+              }
+            }
+          } else {
+            for (int z = 0; z < a.fin.nblk; ++z) {
+              const float* tb = stage + z * (4 * C + T);
+              const float cn = tb[4 * C + t];
+              float dv[C];
+              if (a.fin.unfolded) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) dv[c] = 0.f;
+                const int Lz = a.fin.L[z], sz = a.fin.stride[z], wz = a.fin.w[z];
+                for (int j = 0; j < wz; ++j) {
+                  const int d = t - j;
+                  if (d < 0 || d % sz || d / sz >= Lz) continue;
+                  float pv[C];
+                  load_row<C>(a.fin.dxp[z] + ((((size_t)b * Lz + d / sz) * wz + j) * N + n) * C, pv);
+#pragma unroll
+                  for (int c = 0; c < C; ++c) dv[c] += pv[c];
+                }
+              } else {
+                load_row<C>(a.fin.dxp[z] + (size_t)r * C, dv);
+              }
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const float xh = (xv[c] - tb[c]) * tb[C + c];
+                dhv[c] += dv[c] - cn * (tb[2 * C + c] + xh * tb[3 * C + c]);
+              }
             }
           }
           store_row<C>(a.fin.dh_out + (size_t)r * C, dhv);
@@ -399,58 +488,73 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
           load_row<C>(a.dh + (size_t)r * C, dhv);
         }
       }
+      ENC_STAMP(4)
+      float st[2 * C];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         float dhn = 0.f, zh = 0.f;
         if (act) {
-          dhn = dhv[c] * keep_scale_f(a, kbase + c);
-          zh = (z3t[c * kT] - mu3[c]) * r3[c];
+          dhn = dhv[c] * drop_scale(a, dkey, krow, C, c);
+          zh = (z3[c] - mu3[c]) * r3[c];
         }
-        stat_add_f(sacc, c, dhn);
-        stat_add_f(sacc, C + c, dhn * zh);
+        st[c] = dhn;
+        st[C + c] = dhn * zh;
       }
+      ENC_STAMP(5)
+      stat_flush<2 * C>(sacc, st);
+      ENC_STAMP(6)
     } else if constexpr (PH == 5) {
       float* sdz = stage;                 // [C][kTP]
       float* sa2 = stage + C * kTP;       // [EL2][kTP]
       float dz[C];
-      const size_t kbase = ((size_t)(b * N + n) * T + t) * C;
+      const size_t krow = (size_t)(b * N + n) * T + t;
+      const unsigned long long dkey = drop_row_key(a, krow);
+      // the row's inputs first (one round trip to memory), arithmetic afterwards
+      float c2v[EL2];
       {
-        float dhv[C];
+        float dhv[C], z3[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { dhv[c] = 0.f; z3[c] = act ? z3t[c * kLP] : 0.f; }
         if (act) load_row<C>(a.dh + (size_t)r * C, dhv);
+#pragma unroll
+        for (int k = 0; k < EL2; ++k) c2v[k] = act ? c2t[k * kLP] : 0.f;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           float v = 0.f;
           if (act) {
-            const float dhn = dhv[c] * keep_scale_f(a, kbase + c);
-            const float zh = (z3t[c * kT] - mu3[c]) * r3[c];
+            const float dhn = dhv[c] * drop_scale(a, dkey, krow, C, c);
+            const float zh = (z3[c] - mu3[c]) * r3[c];
             v = A3[c] * (dhn - q3[c] - zh * q3[C + c]);
           }
           dz[c] = v;
           sdz[c * kTP + tid] = v;
         }
       }
+      ENC_STAMP(4)
+      float st[2 * E];
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         float s = 0.f, sh = 0.f;
 #pragma unroll
         for (int p = 0; p < L2; ++p) {
           const int k = e * L2 + p;
-          const float c2v = act ? c2t[k * kT] : 0.f;
-          const float a2v = act ? fmaxf(fmaf(A2[e], c2v, C2[e]), 0.f) : 0.f;
+          const float a2v = act ? fmaxf(fmaf(A2[e], c2v[k], C2[e]), 0.f) : 0.f;
           sa2[k * kTP + tid] = a2v;
           float v = 0.f;
-          if (a2v > 0.f) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) v = fmaf(dz[c], W3[c * EL2 + k], v);
-          }
-          dn2t[k * kT] = v;
+          for (int c = 0; c < C; ++c) v = fmaf(dz[c], W3[c * EL2 + k], v);
+          v = a2v > 0.f ? v : 0.f;
+          dn2t[k * kLP] = v;
           s += v;
-          sh = fmaf(v, (c2v - mu2[e]) * r2[e], sh);
+          sh = fmaf(v, (c2v[k] - mu2[e]) * r2[e], sh);
         }
-        stat_add_f(sacc, e, s);
-        stat_add_f(sacc, E + e, sh);
+        st[e] = s;
+        st[E + e] = sh;
       }
+      ENC_STAMP(5)
+      stat_flush<2 * E>(sacc, st);
       __syncthreads();
+      ENC_STAMP(6)
       pair_reduce_f<C * EL2 + C>(accW, [&](int pair, int r4) {
         if (pair >= C * EL2) {
           const float4 d = ld4(sdz + (pair - C * EL2) * kTP + r4);
@@ -464,17 +568,23 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
       float* sdc = stage;                 // [EL2][kTP]
       float* sa1 = stage + EL2 * kTP;     // [NL1][kTP]
       float dc2[EL2];
+      {
+        float c2v[EL2], dnv[EL2];
 #pragma unroll
-      for (int k = 0; k < EL2; ++k) {
-        const int e = k / L2;
-        float v = 0.f;
-        if (act) {
-          const float ch2 = (c2t[k * kT] - mu2[e]) * r2[e];
-          v = A2[e] * (dn2t[k * kT] - q2[e] - ch2 * q2[E + e]);
+        for (int k = 0; k < EL2; ++k) { c2v[k] = act ? c2t[k * kLP] : 0.f; dnv[k] = act ? dn2t[k * kLP] : 0.f; }
+#pragma unroll
+        for (int k = 0; k < EL2; ++k) {
+          const int e = k / L2;
+          float v = 0.f;
+          if (act) {
+            const float ch2 = (c2v[k] - mu2[e]) * r2[e];
+            v = A2[e] * (dnv[k] - q2[e] - ch2 * q2[E + e]);
+          }
+          dc2[k] = v;
+          sdc[k * kTP + tid] = v;
         }
-        dc2[k] = v;
-        sdc[k * kTP + tid] = v;
       }
+      float st[2 * EH];
 #pragma unroll
       for (int ch = 0; ch < EH; ++ch) {
         float s = 0.f, sh = 0.f;
@@ -483,22 +593,22 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
           const float a1v = act ? fmaxf(fmaf(A1[ch], c1[ch * L1 + q], C1[ch]), 0.f) : 0.f;
           sa1[(ch * L1 + q) * kTP + tid] = a1v;
           float v = 0.f;
-          if (a1v > 0.f) {
 #pragma unroll
-            for (int e = 0; e < E; ++e)
+          for (int e = 0; e < E; ++e)
 #pragma unroll
-              for (int j = 0; j < K; ++j) {
-                const int p = q - j + 1;
-                if (p >= 0 && p < L2) v = fmaf(dc2[e * L2 + p], W2[(e * EH + ch) * K + j], v);
-              }
-          }
-          dn1t[(ch * L1 + q) * kT] = v;
+            for (int j = 0; j < K; ++j) {
+              const int p = q - j + 1;
+              if (p >= 0 && p < L2) v = fmaf(dc2[e * L2 + p], W2[(e * EH + ch) * K + j], v);
+            }
+          v = a1v > 0.f ? v : 0.f;
+          dn1t[(ch * L1 + q) * kLP] = v;
           s += v;
           sh = fmaf(v, (c1[ch * L1 + q] - mu1[ch]) * r1[ch], sh);
         }
-        stat_add_f(sacc, ch, s);
-        stat_add_f(sacc, EH + ch, sh);
+        st[ch] = s;
+        st[EH + ch] = sh;
       }
+      stat_flush<2 * EH>(sacc, st);
       __syncthreads();
       pair_reduce_f<E * EH * K>(accW, [&](int pair, int r4) {
         const int j = pair % K, ech = pair / K, ch = ech % EH, e = ech / EH;
@@ -514,15 +624,20 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
     } else if constexpr (PH == 7) {
       float* sdc = stage;                 // [NL1][kTP]
       float* sx = stage + NL1 * kTP;      // [P][kTP]
+      {
+        float dnv[NL1];
 #pragma unroll
-      for (int i = 0; i < NL1; ++i) {
-        const int ch = i / L1;
-        float v = 0.f;
-        if (act) {
-          const float ch1 = (c1[i] - mu1[ch]) * r1[ch];
-          v = A1[ch] * (dn1t[i * kT] - q1[ch] - ch1 * q1[EH + ch]);
+        for (int i = 0; i < NL1; ++i) dnv[i] = act ? dn1t[i * kLP] : 0.f;
+#pragma unroll
+        for (int i = 0; i < NL1; ++i) {
+          const int ch = i / L1;
+          float v = 0.f;
+          if (act) {
+            const float ch1 = (c1[i] - mu1[ch]) * r1[ch];
+            v = A1[ch] * (dnv[i] - q1[ch] - ch1 * q1[EH + ch]);
+          }
+          sdc[i * kTP + tid] = v;
         }
-        sdc[i * kTP + tid] = v;
       }
 #pragma unroll
       for (int i = 0; i < P; ++i) sx[i * kTP + tid] = x[i];
@@ -541,6 +656,7 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
     }
   }
   __syncthreads();
+  ENC_STAMP(2)
   constexpr int nstat = PH == 0 ? EH : PH == 1 ? E : PH == 2 ? C : PH == 4 ? C : PH == 5 ? E : PH == 6 ? EH : 0;
   if (nstat) {
     double* dst = PH == 0 ? a.st : PH == 1 ? a.st + 2 * EH : PH == 2 ? a.st + 2 * (EH + E) : PH == 4 ? Bq3 : PH == 5 ? Bq2 : Bq1;
@@ -559,6 +675,10 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : 3) k_enc_fast(const EncArgs 
   } else if (PH == 7) {
     for (int i = tid; i < EH * K; i += kT) atomicAdd(&a.dW1[i], accW[i]);
   }
+#ifdef STG_ENC_TIMING
+  __syncthreads();
+  ENC_STAMP(3)
+#endif
 }
 
 template <class D, int PH>
@@ -595,12 +715,12 @@ void launch_one(const EncArgs& a, cudaStream_t s) {
     attr_done = true;
   }
   const int ntiles = (a.R + kT - 1) / kT;
-  int per_sm = smem > 56 * 1024 ? 2 : smem > 40 * 1024 ? 4 : 6;
+  int per_sm = smem > 56 * 1024 ? 2 : smem > 24 * 1024 ? 4 : 8;
   if (const char* e = getenv("STG_ENC_PERSM")) { const int v = atoi(e); if (v >= 1) per_sm = v; }
   int grid = sms_f() * per_sm;
   if (grid > ntiles) grid = ntiles;
   ProfScope ps(kProfOfF[PH], s);
-  k_enc_fast<D, PH><<<grid, kT, smem, s>>>(a);
+  launch_pdl(k_enc_fast<D, PH>, dim3(grid), dim3(kT), smem, s, a);
 }
 
 template <class D>
@@ -635,6 +755,12 @@ using D_FD002 = EncDims<1, 2, 8, 12, 16>;  // hparams.py:69-71
 using D_FD003 = EncDims<1, 2, 8, 6, 48>;   // hparams.py:109-111
 
 }  // namespace
+
+#ifdef STG_ENC_TIMING
+extern "C" int stg_debug_enc_cta_times(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_enc_time, sizeof(g_enc_time)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 bool encoder_fast_available(const EncArgs& a) {
   static const bool off = getenv("STG_ENC_GENERIC") != nullptr;      // tests: force the any-dimension kernels

@@ -43,6 +43,7 @@ STG_DEVINL void head_bn1(const HeadArgs& a, float (*c)[4][64], bool update_runni
 // (GraphConvpoolMPNN_block_v6 tail, Model_Base.py:103-107,212-216) and written to feat_out.
 template <int JP, int SPB, bool FUSED>
 __global__ void __launch_bounds__(256) k_head_fc1(const HeadArgs a, int kper) {
+  pdl_sync();
   __shared__ float red[8][SPB * JP];
   __shared__ float bc[2][4][64];
   const int b0 = blockIdx.x * SPB, tid = threadIdx.x, J = a.J, F = a.F;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256) k_head_fc1(const HeadArgs a, int kper) {
 // MODE 0: forward only (pred).  MODE 1: backward with given dpred.  MODE 2: fused MSE + backward.
 template <int MODE>
 __global__ void __launch_bounds__(128) k_head_tail(const HeadArgs a, int TB) {
+  pdl_sync();
   extern __shared__ __align__(16) float sm[];
   const int J = a.J, H = a.H, tid = threadIdx.x, nt = blockDim.x;
   const int TBP = TB + 1;
@@ -370,6 +372,7 @@ static size_t tail_slice_floats(int J, int H, int nb) {
 //   stats[2H+h] += sum dYn, stats[3H+h] += sum dYn*Yhat, with dYn = dfeat/w * lrelu'(BN1(Y')).
 template <int JP, bool FUSED, int TAIL>      // TAIL: 0 = d1 given, 1 = tail from dpred, 2 = tail with MSE loss
 __global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
+  pdl_sync();
   extern __shared__ __align__(16) float sm[];   // d1 slice [bper][J] (+ tail scratch)
   __shared__ float bc[2][4][64];
   __shared__ float sred[2][2][64];
@@ -462,6 +465,7 @@ __global__ void __launch_bounds__(128) k_head_bwd1(const HeadArgs a, int bper) {
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long long n, const long long* __restrict__ step,
                                               float lr, float b1, float b2, float eps, float wd, float gscale) {
+  pdl_sync();
   __shared__ float s_bc[2];
   if (threadIdx.x == 0) {                      // bias corrections once per CTA (double pow is slow)
     const double t = (double)(*step);
@@ -485,12 +489,14 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
 
 struct TickArgs { long long* p[16]; int n; float* zero1; };
 __global__ void k_tick(const TickArgs t) {
+  pdl_sync();
   if (threadIdx.x < t.n && t.p[threadIdx.x]) *t.p[threadIdx.x] += 1;
 }
 
 // first kernel of a step: clears the reduction scratch, increments the step counters
 // (num_batches_tracked, dropout counter) and clears one extra word (the caller's loss accumulator)
 __global__ void __launch_bounds__(256) k_zero(float4* p, size_t n4, const TickArgs t) {
+  pdl_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
     p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (blockIdx.x == 0) {
@@ -513,6 +519,7 @@ constexpr int kWFP = kWBM + 4;      // pitch of the transposed feature tile (16-
 // Thread (tx = tid%16, ty = tid/16): JQ = JP/16 outputs j = tx*JQ.. for the 8 samples ty*8.. of the tile.
 template <int JP, bool FUSED>
 __global__ void __launch_bounds__(kWT) k_head_fc1_wide(const HeadArgs a, int kper) {
+  pdl_sync();
   constexpr int JQ = JP / 16;
   __shared__ __align__(16) float fT[kWKC][kWFP];     // feat tile, [k][sample]
   __shared__ float Ws[JP][kWKC + 1];                 // W1 tile, [j][k]
@@ -596,6 +603,7 @@ __global__ void __launch_bounds__(kWT) k_head_fc1_wide(const HeadArgs a, int kpe
 constexpr int kWBC = 64;            // samples per chunk (bwd1)
 template <int JP, bool FUSED>
 __global__ void __launch_bounds__(kWT, 2) k_head_bwd1_wide(const HeadArgs a) {
+  pdl_sync();
   constexpr int JR = JP / 8;
   extern __shared__ __align__(16) float sm[];
   float* Ws = sm;                         // [JP][128]
@@ -746,8 +754,8 @@ void fc1_wide_launch(const HeadArgs& a, cudaStream_t s) {
   if (ksplit < 1) ksplit = 1;
   const int kper = (((a.F + ksplit - 1) / ksplit) + kWKC - 1) / kWKC * kWKC;
   ksplit = (a.F + kper - 1) / kper;
-  if (a.fused_blocks) k_head_fc1_wide<JP, true><<<dim3(gx, ksplit), kWT, 0, s>>>(a, kper);
-  else k_head_fc1_wide<JP, false><<<dim3(gx, ksplit), kWT, 0, s>>>(a, kper);
+  if (a.fused_blocks) launch_pdl(k_head_fc1_wide<JP, true>, dim3(gx, ksplit), dim3(kWT), 0, s, a, kper);
+  else launch_pdl(k_head_fc1_wide<JP, false>, dim3(gx, ksplit), dim3(kWT), 0, s, a, kper);
 }
 template <int JP>
 void bwd1_wide_launch(const HeadArgs& a, cudaStream_t s) {
@@ -759,8 +767,8 @@ void bwd1_wide_launch(const HeadArgs& a, cudaStream_t s) {
     attr_done = true;
   }
   const int gx = (a.F + 127) / 128;
-  if (a.fused_blocks) k_head_bwd1_wide<JP, true><<<gx, kWT, smem, s>>>(a);
-  else k_head_bwd1_wide<JP, false><<<gx, kWT, smem, s>>>(a);
+  if (a.fused_blocks) launch_pdl(k_head_bwd1_wide<JP, true>, dim3(gx), dim3(kWT), smem, s, a);
+  else launch_pdl(k_head_bwd1_wide<JP, false>, dim3(gx), dim3(kWT), smem, s, a);
 }
 inline bool head_wide(const HeadArgs& a) {
   static const bool off = getenv("STG_HEAD_NARROW") != nullptr;
@@ -777,8 +785,8 @@ void fc1_launch(const HeadArgs& a, cudaStream_t s) {
   if (ksplit < 1) ksplit = 1;
   const int kper = (((a.F + ksplit - 1) / ksplit) + 3) / 4 * 4;
   ksplit = (a.F + kper - 1) / kper;
-  if (a.fused_blocks) k_head_fc1<JP, SPB, true><<<dim3(gx, ksplit), 256, 0, s>>>(a, kper);
-  else k_head_fc1<JP, SPB, false><<<dim3(gx, ksplit), 256, 0, s>>>(a, kper);
+  if (a.fused_blocks) launch_pdl(k_head_fc1<JP, SPB, true>, dim3(gx, ksplit), dim3(256), 0, s, a, kper);
+  else launch_pdl(k_head_fc1<JP, SPB, false>, dim3(gx, ksplit), dim3(256), 0, s, a, kper);
 }
 template <int JP>
 void bwd1_launch(const HeadArgs& a, cudaStream_t s) {
@@ -801,10 +809,10 @@ void bwd1_launch(const HeadArgs& a, cudaStream_t s) {
   if (a.fused_blocks) {
     // model path: the tail (fc2..fc4, loss, its backward) is recomputed per slice inside this kernel
     const size_t smt = sm_d1 + tail_slice_floats(a.J, a.H, bper) * 4;
-    if (a.y) k_head_bwd1<JP, true, 2><<<dim3(gx, slices), 128, smt, s>>>(a, bper);
-    else k_head_bwd1<JP, true, 1><<<dim3(gx, slices), 128, smt, s>>>(a, bper);
+    if (a.y) launch_pdl(k_head_bwd1<JP, true, 2>, dim3(gx, slices), dim3(128), smt, s, a, bper);
+    else launch_pdl(k_head_bwd1<JP, true, 1>, dim3(gx, slices), dim3(128), smt, s, a, bper);
   } else {
-    k_head_bwd1<JP, false, 0><<<dim3(gx, slices), 128, sm_d1, s>>>(a, bper);
+    launch_pdl(k_head_bwd1<JP, false, 0>, dim3(gx, slices), dim3(128), sm_d1, s, a, bper);
   }
 }
 
@@ -837,7 +845,7 @@ int launch_head_forward(const HeadArgs& a, cudaStream_t s) {
     tail_attrs();
     const int TB = tail_tb(a.J);
     ProfScope ps(kProfHeadTail, s);
-    k_head_tail<0><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
+    launch_pdl(k_head_tail<0>, dim3((a.B + TB - 1) / TB), dim3(128), tail_smem(a.J, a.H, TB), s, a, TB);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
@@ -849,8 +857,8 @@ int launch_head_backward(const HeadArgs& a, cudaStream_t s) {
   const bool wide = head_wide(a);
   if (!a.fused_blocks || wide) {         // op path / wide heads: separate tail kernel writes d1
     ProfScope ps(kProfHeadTail, s);
-    if (a.y) k_head_tail<2><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
-    else k_head_tail<1><<<(a.B + TB - 1) / TB, 128, tail_smem(a.J, a.H, TB), s>>>(a, TB);
+    if (a.y) launch_pdl(k_head_tail<2>, dim3((a.B + TB - 1) / TB), dim3(128), tail_smem(a.J, a.H, TB), s, a, TB);
+    else launch_pdl(k_head_tail<1>, dim3((a.B + TB - 1) / TB), dim3(128), tail_smem(a.J, a.H, TB), s, a, TB);
   }
   ProfScope ps(kProfHeadBwd1, s);
   if (wide) { if (a.J <= 48) bwd1_wide_launch<48>(a, s); else bwd1_wide_launch<64>(a, s); }
@@ -872,7 +880,7 @@ int launch_zero(void* p, size_t bytes, long long* const* counters, int ncounters
   for (int i = 0; i < t.n; ++i) t.p[i] = counters[i];
   t.zero1 = zero1;
   ProfScope ps(kProfZero, s);
-  k_zero<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(p), n4, t);
+  launch_pdl(k_zero, dim3(grid), dim3(256), 0, s, reinterpret_cast<float4*>(p), n4, t);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -881,11 +889,11 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, long 
   TickArgs t = {};
   t.p[0] = step;
   t.n = 1;
-  k_tick<<<1, 32, 0, s>>>(t);
+  launch_pdl(k_tick, dim3(1), dim3(32), 0, s, t);
   int grid = (int)((n + 255) / 256);
   if (grid > 1184) grid = 1184;
   ProfScope ps(kProfAdam, s);
-  k_adam<<<grid, 256, 0, s>>>(p, g, m, v, n, step, lr, b1, b2, eps, wd, gscale);
+  launch_pdl(k_adam, dim3(grid), dim3(256), 0, s, p, g, m, v, n, step, lr, b1, b2, eps, wd, gscale);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -893,7 +901,7 @@ int launch_tick(long long* const* counters, int n, cudaStream_t s) {
   TickArgs t = {};
   t.n = n > 16 ? 16 : n;
   for (int i = 0; i < t.n; ++i) t.p[i] = counters[i];
-  k_tick<<<1, 32, 0, s>>>(t);
+  launch_pdl(k_tick, dim3(1), dim3(32), 0, s, t);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

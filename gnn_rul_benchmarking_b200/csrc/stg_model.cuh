@@ -50,6 +50,28 @@ struct EncArgs {
 inline __host__ __device__ int enc_stats_doubles(int EH, int E, int C) { return 4 * (EH + E + C); }
 
 int plan_encoder(EncArgs& a, size_t* smem_fwd, size_t* smem_bwd, char* err, size_t errlen);
+// Dropout of the encoder output without a mask tensor (forward and backward re-derive the same decisions): one
+// 64-bit mix per row of (seed, step counter, row), then one 32-bit mix per element of the row.
+__device__ __forceinline__ unsigned long long drop_row_key(const EncArgs& a, size_t row) {
+  unsigned long long z = a.seed + (a.seed_ptr ? (unsigned long long)*a.seed_ptr * 0xD1B54A32D192ED03ull : 0ull) +
+                         (unsigned long long)row * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// keep / (1 - p) scale of element c of the row (C elements per row); 1 outside training
+__device__ __forceinline__ float drop_scale(const EncArgs& a, unsigned long long key, size_t row, int C, int c) {
+  if (!a.training || a.pdrop <= 0.f) return 1.f;
+  const float sc = 1.f / (1.f - a.pdrop);
+  if (a.keep) return a.keep[row * C + c] * sc;
+  unsigned h = (unsigned)key ^ ((unsigned)(key >> 32) + (unsigned)c * 0x9E3779B9u);
+  h ^= h >> 16; h *= 0x85EBCA6Bu;
+  h ^= h >> 13; h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  const float u = (float)(h >> 8) * (1.f / 16777216.f);
+  return u >= a.pdrop ? sc : 0.f;
+}
+
 int launch_encoder_forward(const EncArgs& a, size_t smem, cudaStream_t s);
 int launch_encoder_backward(const EncArgs& a, size_t smem, cudaStream_t s);
 // compile-time-dimension variants (stg_encoder_fast.cu) for the register-sized hyper-parameter sets

@@ -145,6 +145,7 @@ struct SmemLayout {
   int wcb;     // [4][32][4]    projection weights  B[n = o][k = c], K-major
   int wc2;     // [6][16][4]    [Wm ; a0 Wtheta]    B[n = c][k = o], K-major
   int wc2l;    // SPLIT: its residual
+  int pf_fv, pf_p;   // backward prefetch staging: the tile's saved F|V blocks and softmax blocks
   int cst;     // constants (floats)
   int total;
 };
@@ -157,7 +158,9 @@ constexpr int kCstMisc = 160;      // decay
 constexpr int kCstRed = 176;       // backward: G[24][17], dbt[8], per-warp partials [4][32]; forward: partials [4][16]
 constexpr int kCstFloats = 176 + 24 * 17 + 8 + 128 + 8;
 
-__host__ __device__ inline SmemLayout make_layout(int WR, bool bwd, bool split) {
+// pfM > 0 (backward only): stage the tile's saved F|V and softmax blocks (w*N = pfM rows per window) in shared memory
+// with 1-D TMA bulk copies issued one tile ahead.
+__host__ __device__ inline SmemLayout make_layout(int WR, bool bwd, bool split, int pfM = 0) {
   SmemLayout l;
   int o = 0;
   // forward: x / F rows (K-major, + residuals), V rows, projection weights.  backward: row records, dY' | V rows,
@@ -169,7 +172,9 @@ __host__ __device__ inline SmemLayout make_layout(int WR, bool bwd, bool split) 
   l.rb = o; if (bwd) o += 128 * 128;
   l.yk = o; if (bwd) o += 2 * 2 * 128 * 16;
   l.t1 = o; if (bwd) o += 4 * WR * 128;
-  l.t2 = o; if (bwd) o += (4 * WR * 128 > 28 * 1024 ? 4 * WR * 128 : 28 * 1024);
+  l.t2 = o; if (bwd) o += (4 * WR * 128 > 24 * 1024 ? 4 * WR * 128 : 24 * 1024);      // later: K-major rows 12 KB + residuals 12 KB
+  l.pf_fv = o; if (bwd && pfM) o += (128 / WR) * kCPH * pfM * 4;
+  l.pf_p = o; if (bwd && pfM) o += ((128 / WR) * (pfM + 1) * pfM * 4 + 15) / 16 * 16;
   l.wcb = o; if (!bwd) o += 4 * 32 * 16;
   l.wcbl = o; if (!bwd && split) o += 4 * 32 * 16;
   l.wc2 = o; if (bwd) o += 6 * 16 * 16;
@@ -193,6 +198,7 @@ __host__ __device__ inline int saved_mp(int M) { return M + 1; }
 
 struct TcCtl {
   uint64_t bar;
+  uint64_t bar_pf;       // backward: completion of the prefetched blocks (TMA bulk copies)
   uint32_t tmem_base;
   uint32_t pad;
 };
