@@ -25,6 +25,29 @@ STG_DEVINL float warp_max(float v) {
   return v;
 }
 
+// Warp totals of NP (power of two, <= 32) per-thread values with a halving butterfly: every exchange step halves the
+// number of live values (NP - 1 shuffles for NP = 32 instead of 5 NP for one warp_sum per value).  Afterwards lane l
+// holds the total of value l / (32 / NP).
+template <int NP>
+STG_DEVINL float warp_multi_sum(float (&w)[NP]) {
+  const int lane = threadIdx.x & 31;
+  int o = 16;
+#pragma unroll
+  for (int n = NP; n > 1; n >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? w[i] : w[i + n / 2];
+      const float keep = up ? w[i + n / 2] : w[i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float r = w[0];
+#pragma unroll
+  for (; o >= 1; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) ---------------------------
 STG_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

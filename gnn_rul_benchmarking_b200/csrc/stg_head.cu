@@ -8,10 +8,28 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include "stg_mma.cuh"
 #include "stg_model.cuh"
 
 namespace stg {
 namespace {
+
+#ifdef STG_HEAD_TIMING
+// debug build only (scripts/head_cta_times.py): clock64 deltas of up to 8 points per CTA, kernel 0 = fc1, 1 = bwd1
+__device__ unsigned long long g_head_time[2][1024][8];
+#define HEAD_STAMP(kid, slot)                                                                            \
+  {                                                                                                      \
+    const unsigned cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                           \
+    if (threadIdx.x == 0 && cta_ < 1024) {                                                               \
+      if (slot == 0) head_t0 = clock64();                                                                \
+      g_head_time[kid][cta_][slot] = slot == 0 ? 1ull : (unsigned long long)(clock64() - head_t0);       \
+    }                                                                                                    \
+  }
+#define HEAD_T0 long long head_t0 = 0;
+#else
+#define HEAD_STAMP(kid, slot)
+#define HEAD_T0
+#endif
 
 // ------------------------------------------------------------------------------------------
 // BN1 coefficients of the graph-conv blocks from their batch moments: c[z][0]=a1 [1]=c1 [2]=mu1 [3]=r1
@@ -507,6 +525,434 @@ __global__ void __launch_bounds__(256) k_zero(float4* p, size_t n4, const TickAr
 
 
 // ------------------------------------------------------------------------------------------
+// Tensor-core head for the usual shape (J <= 16, features fused from the blocks' saved Y', windows of two time
+// steps, H % 8 == 0 so that every aligned group of 8 feature columns is one (window, sensor) of one block): fc1 and
+// its backward as warp-level mma.sync m16n8k8 TF32 products with the 3xTF32 split (fp32-level accuracy).  One warp
+// owns a [16 samples x 32 columns] (forward) or [bper samples x 16 columns] (backward) piece; every global load of
+// the piece is issued before the first use, the K-split partial results meet in shared memory / float atomics.
+// (The one-thread-per-column kernels above spend their time in 16..32 serialized load round trips and in one
+// five-shuffle warp sum per accumulator.)
+STG_DEVINL void head_group(const HeadArgs& a, int k0, int& z, size_t& off, int& h0) {
+  z = (a.nblk > 1 && k0 >= a.blk[1].foff) ? 1 : 0;
+  const HeadBlk& kb = a.blk[z];
+  const int e = k0 - kb.foff;
+  h0 = e % kb.H;
+  const int ln = e / kb.H, n = ln % kb.N, l = ln / kb.N;
+  off = ((size_t)l * kb.M + n) * kb.H + h0;
+}
+
+// grid (ceil(B/16), ceil(F/128)), 4 warps; warp = 32 feature columns (4 k-steps) of 16 samples
+__global__ void __launch_bounds__(128) k_head_fc1_mma(const HeadArgs a) {
+  pdl_sync();
+  __shared__ float bc[2][4][64];
+  __shared__ float red[4][16 * 16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int F = a.F, J = a.J;
+  const int b0 = blockIdx.x * 16;
+  const int kw0 = (blockIdx.y * 4 + warp) * 32;
+  HEAD_T0
+  HEAD_STAMP(0, 0)
+  head_bn1(a, bc, blockIdx.x == 0 && blockIdx.y == 0);
+  __syncthreads();
+  HEAD_STAMP(0, 1)
+  const bool rok[2] = {b0 + g < a.B, b0 + g + 8 < a.B};
+  float y[4][2][2][2];      // [k-step][column t / t+4][row g / g+8][time step of the window]
+  float wv[4][2][2];        // [k-step][n-tile][column]
+  float ca[4][2], cc[4][2];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int k0 = kw0 + ks * 8;
+    const bool kok = k0 < F;
+    int z = 0, h0 = 0;
+    size_t off = 0;
+    if (kok) head_group(a, k0, z, off, h0);
+    const HeadBlk& kb = a.blk[z];
+    const size_t bst = (size_t)kb.L * kb.M * kb.H, jst = (size_t)kb.N * kb.H;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int col = t + 4 * c;
+      ca[ks][c] = bc[z][0][h0 + col];
+      cc[ks][c] = bc[z][1][h0 + col];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const bool ok = kok && rok[r];
+        const float* p = kb.yp + (size_t)(b0 + g + 8 * r) * bst + off + col;
+        y[ks][c][r][0] = ok ? p[0] : 0.f;
+        y[ks][c][r][1] = ok ? p[jst] : 0.f;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int j = nt * 8 + g;
+        wv[ks][nt][c] = (kok && j < J) ? a.W1[(size_t)j * F + k0 + col] : 0.f;
+      }
+    }
+  }
+  float acc[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[nt][q] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int k0 = kw0 + ks * 8;
+    float fv[2][2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float v = 0.f;
+        if (k0 < F && rok[r]) {
+          v = 0.5f * (lrelu(fmaf(ca[ks][c], y[ks][c][r][0], cc[ks][c])) + lrelu(fmaf(ca[ks][c], y[ks][c][r][1], cc[ks][c])));
+          a.feat_out[(size_t)(b0 + g + 8 * r) * F + k0 + t + 4 * c] = v;
+        }
+        fv[c][r] = v;
+      }
+    const FragA A = make_a(fv[0][0], fv[0][1], fv[1][0], fv[1][1]);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) mma3(acc[nt], A, make_b(wv[ks][nt][0], wv[ks][nt][1]));
+  }
+  HEAD_STAMP(0, 2)
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    float* r = red[warp] + nt * 8 + 2 * t;
+    r[g * 16] = acc[nt][0];
+    r[g * 16 + 1] = acc[nt][1];
+    r[(g + 8) * 16] = acc[nt][2];
+    r[(g + 8) * 16 + 1] = acc[nt][3];
+  }
+  __syncthreads();
+  for (int e = tid; e < 256; e += 128) {
+    const int row = e >> 4, j = e & 15;
+    if (j < J && b0 + row < a.B) {
+      float v = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+      if (blockIdx.y == 0) v += a.b1[j];
+      atomicAdd(&a.z1[(size_t)(b0 + row) * J + j], v);
+    }
+  }
+  HEAD_STAMP(0, 3)
+}
+
+// Tail of the head for the (up to) 32 samples of one CTA of 128 threads: fc2..fc4, loss / dpred and the backward of
+// the tail.  Four threads per sample (thread = sample * 4 + part, so a sample stays inside one warp and the layers
+// only need __syncwarp), each computing a quarter of every layer's outputs from the full input vector in registers;
+// the vectors are exchanged through ts ([row][sample], 33-float pitch) and stay there for the parameter gradients.
+// J <= 16, H <= 8, zero padded.  wsm (staged by the CTA): W2[16][17] W3[8][17] W4[8] b2[16] b3[8] b4[1].
+// Result: d1s[sample * J + j] = dLoss/dz1.
+constexpr int kTwP = 17, kTwW3 = 16 * kTwP, kTwW4 = kTwW3 + 8 * kTwP, kTwB2 = kTwW4 + 8, kTwB3 = kTwB2 + 16,
+              kTwB4 = kTwB3 + 8, kTailW = kTwB4 + 1;
+STG_DEVINL void tail_stage(const HeadArgs& a, float* wsm) {
+  const int J = a.J, H = a.H;
+  for (int i = threadIdx.x; i < kTailW; i += blockDim.x) {
+    float v = 0.f;
+    if (i < kTwW3) { const int r = i / kTwP, c = i - r * kTwP; if (r < J && c < J) v = a.W2[r * J + c]; }
+    else if (i < kTwW4) { const int q = i - kTwW3, r = q / kTwP, c = q - r * kTwP; if (r < H && c < J) v = a.W3[r * J + c]; }
+    else if (i < kTwB2) { if (i - kTwW4 < H) v = a.W4[i - kTwW4]; }
+    else if (i < kTwB3) { if (i - kTwB2 < J) v = a.b2[i - kTwB2]; }
+    else if (i < kTwB4) { if (i - kTwB3 < H) v = a.b3[i - kTwB3]; }
+    else v = a.b4[0];
+    wsm[i] = v;
+  }
+}
+constexpr int kTsA1 = 0, kTsA2 = 16, kTsA3 = 32, kTsD3 = 40, kTsD2 = 48, kTsD1 = 64, kTsDp = 80, kTsRows = 81, kTsP = 33;
+template <bool HAVE_Y>
+STG_DEVINL void tail_cta(const HeadArgs& a, int b_lo, int nb, float* d1s, const float* wsm, float* ts, bool owner) {
+  const int J = a.J, tid = threadIdx.x, s = tid >> 2, p = tid & 3, b = b_lo + s;
+  const bool act = s < nb;
+  const float *W2 = wsm, *W3 = wsm + kTwW3, *W4 = wsm + kTwW4, *b2 = wsm + kTwB2, *b3 = wsm + kTwB3;
+  float* tl = ts + s;
+  float a1[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a1[j] = (act && j < J) ? fmaxf(a.z1[(size_t)b * J + j], 0.f) : 0.f;
+  if (p == 0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tl[(kTsA1 + j) * kTsP] = a1[j];
+  }
+  float a2o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {                     // fc2 + ReLU: rows 4p .. 4p+3
+    const int i = p * 4 + q;
+    float v = b2[i];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v = fmaf(W2[i * kTwP + j], a1[j], v);
+    a2o[q] = fmaxf(v, 0.f);
+    tl[(kTsA2 + i) * kTsP] = a2o[q];
+  }
+  __syncwarp();
+  float a2[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a2[j] = tl[(kTsA2 + j) * kTsP];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {                     // fc3 + ReLU: rows 2p, 2p+1
+    const int i = p * 2 + q;
+    float v = b3[i];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v = fmaf(W3[i * kTwP + j], a2[j], v);
+    tl[(kTsA3 + i) * kTsP] = fmaxf(v, 0.f);
+  }
+  __syncwarp();
+  float a3[8], pred = wsm[kTwB4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a3[i] = tl[(kTsA3 + i) * kTsP];
+    pred = fmaf(W4[i], a3[i], pred);
+  }
+  float dp = 0.f, lossv = 0.f;
+  if (act) {
+    if (HAVE_Y) {
+      const float e = pred - a.y[b];
+      if (p == 0) lossv = e * e / (float)a.B;
+      dp = 2.f * e / (float)a.B;
+    } else {
+      dp = a.dpred[b];
+    }
+    if (owner && p == 0 && a.pred) a.pred[b] = pred;
+  }
+  float dd3[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dd3[i] = a3[i] > 0.f ? dp * W4[i] : 0.f;
+  if (p == 0) {
+    tl[kTsDp * kTsP] = dp;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tl[(kTsD3 + i) * kTsP] = dd3[i];
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {                     // through fc3 and the ReLU of fc2: columns 4p .. 4p+3
+    const int j = p * 4 + q;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v = fmaf(dd3[i], W3[i * kTwP + j], v);
+    tl[(kTsD2 + j) * kTsP] = a2o[q] > 0.f ? v : 0.f;
+  }
+  __syncwarp();
+  float dd2[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) dd2[j] = tl[(kTsD2 + j) * kTsP];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {                     // through fc2 and the ReLU of fc1
+    const int j = p * 4 + q;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v = fmaf(dd2[i], W2[i * kTwP + j], v);
+    v = tl[(kTsA1 + j) * kTsP] > 0.f ? v : 0.f;
+    tl[(kTsD1 + j) * kTsP] = v;
+    if (act && j < J) d1s[s * J + j] = v;
+  }
+  if (HAVE_Y && owner) {
+    lossv = warp_sum(lossv);
+    if ((tid & 31) == 0 && lossv != 0.f && a.loss) atomicAdd(a.loss, lossv);
+  }
+}
+
+// parameter gradients of the tail over the (up to 32) samples whose vectors tail_cta left in ts: all threads of the
+// owner CTA, one entry per thread and pass
+STG_DEVINL void tail_param_grads(const HeadArgs& a, const float* ts) {
+  const int J = a.J, H = a.H;
+  for (int e = threadIdx.x; e < 433; e += blockDim.x) {
+    int ra, rb = -1;
+    float* dst = nullptr;
+    if (e < 256) { const int i = e >> 4, j = e & 15; ra = kTsD2 + i; rb = kTsA1 + j; if (i < J && j < J) dst = &a.dW2[i * J + j]; }
+    else if (e < 384) { const int i = (e - 256) >> 4, j = e & 15; ra = kTsD3 + i; rb = kTsA2 + j; if (i < H && j < J) dst = &a.dW3[i * J + j]; }
+    else if (e < 400) { ra = kTsD2 + (e - 384); if (e - 384 < J) dst = &a.db2[e - 384]; }
+    else if (e < 408) { ra = kTsD3 + (e - 400); if (e - 400 < H) dst = &a.db3[e - 400]; }
+    else if (e < 416) { ra = kTsDp; rb = kTsA3 + (e - 408); if (e - 408 < H) dst = &a.dW4[e - 408]; }
+    else if (e == 416) { ra = kTsDp; dst = &a.db4[0]; }
+    else { ra = kTsD1 + (e - 417); if (e - 417 < J) dst = &a.db1[e - 417]; }
+    if (!dst) continue;
+    const float* pa = ts + ra * kTsP;
+    float v = 0.f;
+    if (rb >= 0) {
+      const float* pb = ts + rb * kTsP;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) v = fmaf(pa[r], pb[r], v);
+    } else {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) v += pa[r];
+    }
+    atomicAdd(dst, v);
+  }
+}
+
+// grid (ceil(F/64), ceil(B/bper)), 4 warps; warp = 16 feature columns (two n-tiles) of the slice's bper = 16*MT samples
+template <int TAIL, int MT>
+__global__ void __launch_bounds__(128) k_head_bwd1_mma(const __grid_constant__ HeadArgs a) {
+  pdl_sync();
+  constexpr int bper = 16 * MT;
+  HEAD_T0
+  HEAD_STAMP(1, 0)
+  extern __shared__ __align__(16) float sm[];   // d1 slice [bper][J] + tail scratch
+  __shared__ float bc[2][4][64];
+  __shared__ float sred[2][2][64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int J = a.J, F = a.F;
+  const int b_lo = blockIdx.y * bper, nb = min(a.B - b_lo, bper);
+  static_assert(TAIL == 0 || MT == 2, "the in-kernel tail handles 32 samples with 128 threads");
+  for (int i = tid; i < bper * J; i += 128) sm[i] = (TAIL == 0 && i < nb * J) ? a.d1[(size_t)b_lo * J + i] : 0.f;
+  for (int i = tid; i < 2 * 2 * 64; i += 128) (&sred[0][0][0])[i] = 0.f;
+  float* wsm = sm + ((bper * J + 3) / 4) * 4;
+  float* ts = wsm + (kTailW + 3) / 4 * 4;
+  if (TAIL != 0) tail_stage(a, wsm);
+  head_bn1(a, bc, false);
+  __syncthreads();
+  HEAD_STAMP(1, 1)
+  if (TAIL != 0) {
+    if (TAIL == 2) tail_cta<true>(a, b_lo, nb, sm, wsm, ts, blockIdx.x == 0);
+    else tail_cta<false>(a, b_lo, nb, sm, wsm, ts, blockIdx.x == 0);
+    __syncthreads();
+    if (blockIdx.x == 0) tail_param_grads(a, ts);
+  }
+  HEAD_STAMP(1, 2)
+  const int kc0 = (blockIdx.x * 4 + warp) * 16;
+  // ---- every global load of the piece first
+  float wv[2][2][2];              // W1[ks*8 + t (+4)][column g of n-tile]: B operand of dfeat = d1 . W1
+  float fe[2 * MT][2][2];         // feat[b_lo + ks*8 + t (+4)][column g of n-tile]: B operand of dW1 = d1^T . feat
+  float2 yv[MT][2][2][2];         // Y'[sample g (+8) of m-tile][columns 2t, 2t+1 of n-tile][time step]
+  int zc[2], hc[2];
+  bool nok[2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const int k0 = kc0 + nt * 8;
+    nok[nt] = k0 < F;
+    int z = 0, h0 = 0;
+    size_t off = 0;
+    if (nok[nt]) head_group(a, k0, z, off, h0);
+    zc[nt] = z;
+    hc[nt] = h0;
+    const HeadBlk& kb = a.blk[z];
+    const size_t bst = (size_t)kb.L * kb.M * kb.H, jst = (size_t)kb.N * kb.H;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int j = ks * 8 + t + 4 * c;
+        wv[nt][ks][c] = (nok[nt] && j < J) ? a.W1[(size_t)j * F + k0 + g] : 0.f;
+      }
+#pragma unroll
+    for (int ks = 0; ks < 2 * MT; ++ks)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int b = ks * 8 + t + 4 * c;
+        fe[ks][nt][c] = (nok[nt] && b < nb) ? a.feat[(size_t)(b_lo + b) * F + k0 + g] : 0.f;
+      }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int b = mt * 16 + g + 8 * r;
+        const bool ok = nok[nt] && b < nb;
+        const float* p = kb.yp + (size_t)(b_lo + b) * bst + off + 2 * t;
+        yv[mt][nt][r][0] = ok ? *reinterpret_cast<const float2*>(p) : make_float2(0.f, 0.f);
+        yv[mt][nt][r][1] = ok ? *reinterpret_cast<const float2*>(p + jst) : make_float2(0.f, 0.f);
+      }
+  }
+  // ---- dfeat[b][k] = sum_j d1[b][j] W1[j][k]  and the BatchNorm-1 backward sums of the blocks
+  FragB wf[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) wf[nt][ks] = make_b(wv[nt][ks][0], wv[nt][ks][1]);
+  float s1[2][2], s2[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float c[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[nt][q] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const float* d = sm + (mt * 16 + g) * J + ks * 8 + t;
+      const bool c0 = ks * 8 + t < J, c1 = ks * 8 + t + 4 < J;
+      const FragA A = make_a(c0 ? d[0] : 0.f, c0 ? d[8 * J] : 0.f, c1 ? d[4] : 0.f, c1 ? d[8 * J + 4] : 0.f);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) mma3(c[nt], A, wf[nt][ks]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      if (!nok[nt]) continue;
+      const int k = kc0 + nt * 8 + 2 * t, z = zc[nt], h = hc[nt] + 2 * t;
+      const float a1x = bc[z][0][h], c1x = bc[z][1][h], mux = bc[z][2][h], r1x = bc[z][3][h];
+      const float a1y = bc[z][0][h + 1], c1y = bc[z][1][h + 1], muy = bc[z][2][h + 1], r1y = bc[z][3][h + 1];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int b = mt * 16 + g + 8 * r;
+        if (b >= nb) continue;
+        const float dx = c[nt][2 * r], dy = c[nt][2 * r + 1];
+        *reinterpret_cast<float2*>(a.dfeat + (size_t)(b_lo + b) * F + k) = make_float2(dx, dy);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float2 yy = yv[mt][nt][r][j];
+          const float gx = dx * 0.5f * (fmaf(a1x, yy.x, c1x) > 0.f ? 1.f : kLeaky);
+          const float gy = dy * 0.5f * (fmaf(a1y, yy.y, c1y) > 0.f ? 1.f : kLeaky);
+          s1[nt][0] += gx;
+          s1[nt][1] += gy;
+          s2[nt][0] = fmaf(gx, (yy.x - mux) * r1x, s2[nt][0]);
+          s2[nt][1] = fmaf(gy, (yy.y - muy) * r1y, s2[nt][1]);
+        }
+      }
+    }
+  }
+  HEAD_STAMP(1, 3)
+  // ---- dW1[j][k] += sum_b d1[b][j] feat[b][k]
+  {
+    float gw[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gw[nt][q] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2 * MT; ++ks) {
+      const float* d = sm + (ks * 8 + t) * J + g;
+      const bool j0 = g < J, j1 = g + 8 < J;
+      const FragA A = make_a(j0 ? d[0] : 0.f, j1 ? d[8] : 0.f, j0 ? d[4 * J] : 0.f, j1 ? d[4 * J + 8] : 0.f);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) mma3(gw[nt], A, make_b(fe[ks][nt][0], fe[ks][nt][1]));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      if (!nok[nt]) continue;
+      const int k = kc0 + nt * 8 + 2 * t;
+      if (g < J) {
+        atomicAdd(&a.dW1[(size_t)g * F + k], gw[nt][0]);
+        atomicAdd(&a.dW1[(size_t)g * F + k + 1], gw[nt][1]);
+      }
+      if (g + 8 < J) {
+        atomicAdd(&a.dW1[(size_t)(g + 8) * F + k], gw[nt][2]);
+        atomicAdd(&a.dW1[(size_t)(g + 8) * F + k + 1], gw[nt][3]);
+      }
+    }
+  }
+  HEAD_STAMP(1, 4)
+  // ---- BN1 backward sums: over the 8 sample lanes of the warp, then shared / global atomics
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      float u = s1[nt][p], v = s2[nt][p];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        u += __shfl_xor_sync(0xffffffffu, u, o);
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+      }
+      if (g == 0 && nok[nt]) {
+        atomicAdd(&sred[zc[nt]][0][hc[nt] + 2 * t + p], u);
+        atomicAdd(&sred[zc[nt]][1][hc[nt] + 2 * t + p], v);
+      }
+    }
+  __syncthreads();
+  for (int i = tid; i < a.nblk * 64; i += 128) {
+    const int z = i >> 6, h = i & 63;
+    const HeadBlk& kb = a.blk[z];
+    if (h < kb.H) {
+      atomicAdd(&kb.stats[2 * kb.H + h], (double)sred[z][0][h]);
+      atomicAdd(&kb.stats[3 * kb.H + h], (double)sred[z][1][h]);
+    }
+  }
+  HEAD_STAMP(1, 5)
+}
+
+// ------------------------------------------------------------------------------------------
 // Wide heads (J > 32, e.g. FD003: F = 24 864, J = 48).  There fc1 and its backward are real GEMMs and the
 // one-thread-per-column kernels above run out of registers / re-read W1 once per sample; these versions tile
 // them through shared memory with register blocking.
@@ -775,6 +1221,16 @@ inline bool head_wide(const HeadArgs& a) {
   return !off && a.J > 32 && a.F >= 2048;
 }
 
+// tensor-core head: see k_head_fc1_mma
+inline bool head_mma(const HeadArgs& a) {
+  static const bool off = getenv("STG_HEAD_SIMT") != nullptr;
+  if (off || !a.fused_blocks || a.J > 16 || a.H > 8 || a.F % 8 || a.nblk < 1) return false;
+  for (int z = 0; z < a.nblk; ++z)
+    if (a.blk[z].w != 2 || a.blk[z].H % 8 || a.blk[z].H > 64 || a.blk[z].foff % 8) return false;
+  return true;
+}
+constexpr int kBwd1MT = 2;      // backward sample slice = 32 samples
+
 template <int JP, int SPB>
 void fc1_launch(const HeadArgs& a, cudaStream_t s) {
   const int gx = (a.B + SPB - 1) / SPB;
@@ -831,11 +1287,18 @@ void tail_attrs() {
 
 }  // namespace
 
+#ifdef STG_HEAD_TIMING
+extern "C" int stg_debug_head_cta_times(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_head_time, sizeof(g_head_time)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int launch_head_forward(const HeadArgs& a, cudaStream_t s) {
   if (a.J > 64 || a.H > 64) return -2;
   {
     ProfScope ps(kProfHeadFc1, s);
     if (head_wide(a)) { if (a.J <= 48) fc1_wide_launch<48>(a, s); else fc1_wide_launch<64>(a, s); }
+    else if (head_mma(a)) launch_pdl(k_head_fc1_mma, dim3((a.B + 15) / 16, (a.F + 127) / 128), dim3(128), 0, s, a);
     else if (a.J <= 16) fc1_launch<16, 2>(a, s);
     else if (a.J <= 32) fc1_launch<32, 2>(a, s);
     else if (a.J <= 48) fc1_launch<48, 1>(a, s);
@@ -862,6 +1325,13 @@ int launch_head_backward(const HeadArgs& a, cudaStream_t s) {
   }
   ProfScope ps(kProfHeadBwd1, s);
   if (wide) { if (a.J <= 48) bwd1_wide_launch<48>(a, s); else bwd1_wide_launch<64>(a, s); }
+  else if (head_mma(a)) {
+    constexpr int bper = 16 * kBwd1MT;
+    const size_t smem = ((size_t)((bper * a.J + 3) / 4) * 4 + (kTailW + 3) / 4 * 4 + kTsRows * kTsP) * 4;
+    const dim3 grid((a.F + 63) / 64, (a.B + bper - 1) / bper);
+    if (a.y) launch_pdl(k_head_bwd1_mma<2, kBwd1MT>, grid, dim3(128), smem, s, a);
+    else launch_pdl(k_head_bwd1_mma<1, kBwd1MT>, grid, dim3(128), smem, s, a);
+  }
   else if (a.J <= 16) bwd1_launch<16>(a, s);
   else if (a.J <= 32) bwd1_launch<32>(a, s);
   else if (a.J <= 48) bwd1_launch<48>(a, s);
