@@ -126,6 +126,14 @@ MODEL_SIGNATURES["stg_gat_backward"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_vo
                                                   C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                   C.c_void_p])
+MODEL_SIGNATURES["stg_rnn_batch_tile"] = (C.c_int, [C.c_int])
+MODEL_SIGNATURES["stg_rnn_saved_floats"] = (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int])
+MODEL_SIGNATURES["stg_rnn_forward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                                 C.c_void_p, C.c_void_p])
+MODEL_SIGNATURES["stg_rnn_backward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                                  C.c_void_p, C.c_void_p])
 SIGNATURES.update(MODEL_SIGNATURES)
 
 _lib = None

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from .primitives import extract_features, gat_attention
+from .rnn import LSTM
 
 
 class GraphAttentionLayer(nn.Module):
@@ -46,7 +47,7 @@ class GAT_LSTM_model(nn.Module):
         lstm_hidden_dim = [hidden_dim[-1]] + list(lstm_hidden_dim)
         self.gat_layers = nn.ModuleList([GraphAttentionLayer(hidden_dim[i], hidden_dim[i + 1], dropout, alpha)
                                          for i in range(len(hidden_dim) - 1)])
-        self.lstm_layers = nn.ModuleList([nn.LSTM(lstm_hidden_dim[i], lstm_hidden_dim[i + 1], num_layers=1, batch_first=True)
+        self.lstm_layers = nn.ModuleList([LSTM(lstm_hidden_dim[i], lstm_hidden_dim[i + 1], num_layers=1, batch_first=True)
                                           for i in range(len(lstm_hidden_dim) - 1)])
         self.fc = nn.Linear(lstm_hidden_dim[-1] * num_patch, 1)
         # Model.py:144-148: identity + first off-diagonals (path graph over the patches).  Constant, so it is

@@ -3,8 +3,10 @@
 the KL term; state dicts interchange).
 
 Native (libstgconv_b200.so): the cosine adjacency (stg_adj_*) and every dense aggregation A.X of the GIN and
-SAGPool layers (stg_agg_*, forward and backward wrt both A and X).  The bidirectional LSTM encoder is cuDNN
-nn.LSTM, the projections library GEMMs; node ranking (sort / gather) stays index arithmetic in torch.  No CPU path.
+SAGPool layers (stg_agg_*, forward and backward wrt both A and X), and the recurrence of the three bidirectional
+LSTMs (stg_rnn_*, rnn.LSTM: persistent kernels with W_hh in registers -- the reference's layout makes the SEQUENCE
+bs*N steps long with a batch of num_patch, the worst case for a launch-per-step library).  Projections are library
+GEMMs; node ranking (sort / gather) stays index arithmetic in torch.  No CPU path.
 """
 from __future__ import annotations
 
@@ -13,6 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .primitives import cosine_distance, graph_matmul
+from .rnn import LSTM
 
 
 class GINLayer(nn.Module):
@@ -33,14 +36,14 @@ class Bi_LSTM_Standard(nn.Module):
     def __init__(self, input_dim, num_hidden, time_length):
         super().__init__()
         self.num_hidden, self.input_dim, self.time_length = 16, input_dim, time_length
-        self.bi_lstm1 = nn.LSTM(input_size=input_dim, hidden_size=num_hidden, num_layers=1, batch_first=True,
-                                dropout=0, bidirectional=True)
+        self.bi_lstm1 = LSTM(input_size=input_dim, hidden_size=num_hidden, num_layers=1, batch_first=True,
+                             dropout=0, bidirectional=True)
         self.drop1 = nn.Dropout(p=0.2)
-        self.bi_lstm2 = nn.LSTM(input_size=num_hidden, hidden_size=num_hidden * 2, num_layers=1, batch_first=True,
-                                dropout=0, bidirectional=True)
+        self.bi_lstm2 = LSTM(input_size=num_hidden, hidden_size=num_hidden * 2, num_layers=1, batch_first=True,
+                             dropout=0, bidirectional=True)
         self.drop2 = nn.Dropout(p=0.2)
-        self.bi_lstm3 = nn.LSTM(input_size=num_hidden * 2, hidden_size=num_hidden, num_layers=1, batch_first=True,
-                                bidirectional=True)
+        self.bi_lstm3 = LSTM(input_size=num_hidden * 2, hidden_size=num_hidden, num_layers=1, batch_first=True,
+                             bidirectional=True)
         self.drop3 = nn.Dropout(p=0.2)
 
     @staticmethod

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from .primitives import ChebNet, GCNLayer, compute_adjacency_matrix, gram_adjacency
+from .rnn import GRU
 
 
 class STGNN_model(nn.Module):
@@ -21,7 +22,7 @@ class STGNN_model(nn.Module):
         super().__init__()
         self.num_patch, self.patch_size, self.top_k = num_patch, patch_size, top_k
         self.chebnet = ChebNet(patch_size, hidden_dim, K)
-        self.gru = nn.GRU(hidden_dim, hidden_dim, batch_first=True)
+        self.gru = GRU(hidden_dim, hidden_dim, batch_first=True)
         self.fc = nn.Linear(hidden_dim * num_patch * num_nodes, 1)
 
     def forward(self, x):
@@ -48,7 +49,7 @@ class GRULayer(nn.Module):
 
     def __init__(self, input_dim, hidden_dim, num_layers):
         super().__init__()
-        self.gru = nn.GRU(input_dim, hidden_dim, num_layers, batch_first=True)
+        self.gru = GRU(input_dim, hidden_dim, num_layers, batch_first=True)
 
     def forward(self, x):
         return self.gru(x)[0]

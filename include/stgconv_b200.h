@@ -298,6 +298,28 @@ int stg_gat_backward(const float* Wh_dev, const float* att_w_dev, const float* a
                      int G, int N, int F, const float* out_dev, const float* dout_dev, float* dWh_dev,
                      float* datt_w_dev, float* datt_b_dev, void* stream);
 
+/* Recurrent layer of the sibling models (primitive T2): the time recurrence of ONE nn.LSTM / nn.GRU
+ * layer with zero initial state, one or two directions (models/HAGCN/Model.py:33-73, models/GAT_LSTM/Model.py:129-132,
+ * models/STGNN/Model.py:72,99, models/STMSGCN/Model.py:52-60).  The input projection is a plain GEMM and stays with the
+ * caller:  xg = x . W_ih^T + b_ih + b_hh  (GRU: the n-gate third gets b_in only, b_hn is passed separately because it
+ * sits inside r * (W_hn h + b_hn)).  Gate order as in torch: LSTM i,f,g,o; GRU r,z,n.
+ *   xg   element (b, t, dir, row) at b*xg_bstride + t*xg_tstride + dir*G*H + row      G = 4 (LSTM) / 3 (GRU)
+ *   out  element (b, t, dir, j)   at b*out_bstride + t*out_tstride + dir*H + j        dir 1 runs t = T-1 .. 0
+ *   whh  [ndir][G*H][H] (weight_hh_l0, weight_hh_l0_reverse), bhn [ndir][H] (GRU only)
+ *   saved  stg_rnn_saved_floats() floats written by a training forward, read by the backward (null: inference)
+ * backward: dout (layout of out) -> dxg (layout of xg: LSTM d loss / d xg; GRU planes r, z and d / d(W_hn h + b_hn))
+ * and, GRU only, dnx = d loss / d (n plane of xg), element (b, t, dir, j) at (b*xg_bstride + t*xg_tstride)/3 + dir*H + j.
+ * dW_hh = sum_t dgates_t (x) h_{t-1} is a GEMM of dxg against the shifted outputs and is left to the caller.  H <= 128. */
+enum { STG_RNN_LSTM = 0, STG_RNN_GRU = 1 };
+int stg_rnn_batch_tile(int B);
+size_t stg_rnn_saved_floats(int cell, int T, int B, int H, int ndir);
+int stg_rnn_forward(int cell, const float* xg_dev, int64_t xg_bstride, int64_t xg_tstride, const float* whh_dev,
+                    const float* bhn_dev, int T, int B, int H, int ndir, float* out_dev, int64_t out_bstride,
+                    int64_t out_tstride, float* saved_dev, void* stream);
+int stg_rnn_backward(int cell, const float* whh_dev, const float* saved_dev, const float* dout_dev,
+                     int64_t out_bstride, int64_t out_tstride, int T, int B, int H, int ndir, float* dxg_dev,
+                     int64_t xg_bstride, int64_t xg_tstride, float* dnx_dev, void* stream);
+
 /* Evaluation metrics (utils.py:136-169, called every epoch from trainer.py:119-121): ACCUMULATES into
  * out4_dev (4 doubles, caller zeroes): [0] sum of Score_v1 terms, [1] sum of Score_v2 terms,
  * [2] sum |pred-real|, [3] sum (pred-real)^2.  Score_v2 average, MAE and RMSE follow as
