@@ -7,23 +7,30 @@
 // The input projection x.W_ih^T + b (and its gradients) is a plain GEMM and stays with the caller; what is here is the
 // part no GEMM library can batch: h_t = cell(xg_t + W_hh.h_{t-1}).
 //
-// Work decomposition.  A CTA owns NB sequences of one direction for all T steps.  Thread r = (gate g, unit j) keeps its
-// row of W_hh in REGISTERS for the whole sequence (KP values), the hidden state lives in shared memory as h[b][k] so that
-// one 16-byte broadcast load feeds two packed FFMA2 (pairs over k), the next step's xg row is prefetched before the
-// current step's products, and the gate pre-activations meet in shared memory where thread (unit, sequence) applies the
-// cell and keeps c_t in a register.  H > 64 (HAGCN's 120-wide layer) does not fit the register file with one row per
-// thread at 4H threads, so the hidden units are split over a cluster of 2 CTAs which exchange the new h through
+// Work decomposition.  A CTA owns 8 sequences of one direction for all T steps.  The per-step product
+// gates[G*H, 8] = W_hh[G*H, H] . h[H, 8] runs on warp-level tensor-core tiles (mma.sync m16n8k8 TF32 with the
+// 3-term error-compensated split, fp32-level accuracy): the A fragments -- W_hh, split into hi / lo -- are loaded ONCE and
+// stay in registers for the whole sequence (128 registers per thread at H = 60), the 8 sequences are the N dimension,
+// and the only per-step operand traffic is the hidden state: 2 conflict-free LDS.32 per k-tile.  (First version: one
+// W_hh row per thread and FFMA2 against broadcast LDS.128 of h -- measured 1.72 us per step at H = 60 because a
+// broadcast LDS.128 costs 2.45 cycles per warp on the SM and every FMA pair needed one, scripts/rnn_probe.cu.)
+// The gate pre-activations meet in shared memory, where thread (unit, sequence) applies the cell and keeps c_t in a
+// register; the next step's xg values are prefetched before the products.  H > 64 (HAGCN's 120-wide layer) does not fit
+// one CTA's register file, so the hidden units are split over a cluster of 4 CTAs which exchange the new h through
 // distributed shared memory (double-buffered, one cluster barrier per step).
-// Backward: the same structure with the transposed matrix (thread (g, k) keeps column k of gate g), the activations
-// the forward saved, dgates written in the layout of xg (it IS d loss / d xg), dW_hh left to the caller as a GEMM of
-// dgates against the shifted outputs.
+// Backward: the same structure with the transposed matrix (output rows = units of this CTA, contraction over all
+// gate rows, split over warps into partial sums), the activations the forward saved, dgates written in the layout
+// of xg (it IS d loss / d xg), dW_hh left to the caller as a GEMM of the gate gradients against the shifted outputs.
 #include <math.h>
 
 #include "../../include/stgconv_b200.h"
 #include "stg_common.cuh"
+#include "stg_mma.cuh"
 
 namespace stg {
 namespace {
+
+constexpr int NB = 8;     // sequences per CTA = N of the m16n8k8 tiles
 
 struct RnnArgs {
   const float* xg;      // element (b, t, d, r) at b*gsb + t*gst + d*G*H + r
@@ -32,29 +39,20 @@ struct RnnArgs {
   const float* bhn;     // GRU: [ndir][H] (b_hn stays inside r * (...)), else null
   float* out;           // element (b, t, d, j) at b*osb + t*ost + d*H + j
   long long osb, ost;
-  float* saved;         // [ndir][ntile][T][S][H*NB] or null (inference)
+  float* saved;         // [ndir][ntile][T][S][H*8] or null (inference)
   // backward only
   const float* dout;    // layout of out
-  float* dxg;           // layout of xg: LSTM d/d(xg); GRU planes (r, z, hn)
-  float* dnx;           // GRU: element (b, t, d, j) at (b*gsb + t*gst)/G + d*H + j : d/d(xg n-plane)
+  float* dxg;           // layout of xg: d loss / d xg
+  float* dhn;           // GRU: layout of out: d loss / d (W_hn h + b_hn)
   int T, B, H, Hc, ntile;
 };
 
-STG_DEVINL float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
-
-STG_DEVINL void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
-}
-STG_DEVINL unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-STG_DEVINL float sum2(unsigned long long v) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-  return lo + hi;
-}
+// Accurate-to-3e-7 activations on the MUFU pipe, 4-5 instructions each (the libm tanhf / expf sequences were a third
+// of a step): sigmoid = rcp(1 + ex2(-x log2 e)), tanh = 2 sigmoid(2x) - 1.  Saturate correctly (ex2 -> inf / 0).
+STG_DEVINL float ex2_(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+STG_DEVINL float rcp_(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+STG_DEVINL float sigmoidf_(float v) { return rcp_(1.f + ex2_(-1.4426950408889634f * v)); }
+STG_DEVINL float tanhf_(float v) { return fmaf(2.f, rcp_(1.f + ex2_(-2.8853900817779268f * v)), -1.f); }
 
 template <int CS>
 STG_DEVINL unsigned cluster_rank() {
@@ -88,194 +86,317 @@ STG_DEVINL void st_all(float* p, float v) {
   }
 }
 
-// acc[b] += sum_k w[k] * v[b][k]   (v: [NB][KP] floats in shared memory, 16-byte aligned rows)
-template <int KP, int NB>
-STG_DEVINL void matvec(const unsigned long long (&w2)[KP / 2], const float* v, unsigned long long (&acc)[NB]) {
-#pragma unroll
-  for (int k4 = 0; k4 < KP / 4; ++k4) {
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const ulonglong2 hv = *reinterpret_cast<const ulonglong2*>(v + b * KP + k4 * 4);
-      ffma2(acc[b], w2[2 * k4], hv.x);
-      ffma2(acc[b], w2[2 * k4 + 1], hv.y);
-    }
-  }
-}
-
-__host__ __device__ constexpr int rnn_min_blocks(int KP) { return KP <= 8 ? 4 : (KP <= 32 ? 3 : (KP <= 64 ? 2 : 1)); }
-__host__ __device__ constexpr int rnn_cluster(int KP) { return KP > 64 ? 2 : 1; }
-__host__ __device__ constexpr int rnn_saved_planes(int G) { return G == 4 ? 6 : 5; }
+// Kernel shapes.  KT = k-tiles of 8 covering the hidden size, MT = m-tiles (16 gate rows) per warp in the forward,
+// WARPS per CTA, CS = CTAs per cluster (hidden units split), ITEMS = (unit, sequence) cells per thread.
+template <int KT_> struct RnnCfg;
+template <> struct RnnCfg<1>  { static constexpr int KT = 1,  MT = 1, WARPS = 2, CS = 1, ITEMS = 1; };   // H <= 8
+template <> struct RnnCfg<4>  { static constexpr int KT = 4,  MT = 1, WARPS = 8, CS = 1, ITEMS = 1; };   // H <= 32
+template <> struct RnnCfg<8>  { static constexpr int KT = 8,  MT = 2, WARPS = 8, CS = 1, ITEMS = 2; };   // H <= 64
+template <> struct RnnCfg<16> { static constexpr int KT = 16, MT = 1, WARPS = 8, CS = 4, ITEMS = 1; };   // H <= 128
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int G, int KP, int NB>
-__global__ void __launch_bounds__(256, rnn_min_blocks(KP)) k_rnn_fwd(const RnnArgs a) {
-  constexpr int CS = rnn_cluster(KP);
-  constexpr int S = rnn_saved_planes(G);
-  constexpr int ITEMS = (NB + G - 1) / G;
+// saved activations: [dir][tile][t][unit*8 + sequence][6]  (LSTM: i f g o c c_prev; GRU: r z n hn+b h_prev -)
+constexpr int SP = 6;
+
+template <int G, int KT>
+__global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_fwd(const RnnArgs a) {
+  using Cfg = RnnCfg<KT>;
+  constexpr int CS = Cfg::CS, MT = Cfg::MT, ITEMS = Cfg::ITEMS, NT = Cfg::WARPS * 32;
+  constexpr int KP = KT * 8, KS = KP + 4;                 // h row stride: banks of (sequence, k) pairs distinct
   const int H = a.H, Hc = a.Hc, T = a.T;
   const int crank = (int)cluster_rank<CS>();
   const int tile = blockIdx.x / CS, d = blockIdx.y;
-  const int P = G * Hc, tid = threadIdx.x;
-  const int g = tid / Hc, jl = tid - g * Hc, j = crank * Hc + jl;
-  const bool row_ok = tid < P && j < H;
+  const int P = G * Hc, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, t4 = lane & 3;
   const int b0 = tile * NB;
 
   extern __shared__ float4 sm4[];
-  float* h_s = reinterpret_cast<float*>(sm4);             // [2][NB][KP]
-  float* g_s = h_s + 2 * NB * KP;                         // [GP][Hc*NB]
+  float* h_s = reinterpret_cast<float*>(sm4);             // [2][8][KS]
+  float* g_s = h_s + 2 * NB * KS;                         // [4][Hc*8]: gate planes (GRU: r, z, hn, xn)
 
-  unsigned long long w2[KP / 2];
-  {
-    const float* wr = a.whh + ((size_t)(d * G + g) * H + j) * H;
+  // ---- product role: rows of this thread's C fragments (mt, half) -> gate g, unit j; W_hh fragments, split hi / lo
+  FragA wa[MT][KT];
+  float bhn[MT][2];
+  bool isn[MT][2], rowok[MT][2];
+  const float* xp[MT][4];                                 // running pointers into xg (element e: row half e>>1, sequence 2*t4 + (e&1))
+  bool xok[MT][4];
+  float* gst_p[MT][2];
 #pragma unroll
-    for (int k = 0; k < KP; k += 2)
-      w2[k / 2] = pack2((row_ok && k < H) ? wr[k] : 0.f, (row_ok && k + 1 < H) ? wr[k + 1] : 0.f);
+  for (int i = 0; i < MT; ++i) {
+    int rg[2], rj[2];
+    bool rok[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int row = (warp * MT + i) * 16 + g8 + 8 * hf;
+      rg[hf] = row / Hc;
+      rj[hf] = crank * Hc + (row - rg[hf] * Hc);
+      rok[hf] = row < P && rj[hf] < H;
+      rowok[i][hf] = row < P;
+      isn[i][hf] = (G == 3 && rg[hf] == 2);
+      bhn[i][hf] = (isn[i][hf] && rok[hf]) ? a.bhn[d * H + rj[hf]] : 0.f;
+      gst_p[i][hf] = g_s + row * NB + 2 * t4;
+    }
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int hf = e & 1, k = kt * 8 + t4 + 4 * (e >> 1);
+        v[e] = (rok[hf] && k < H) ? a.whh[((size_t)(d * G + rg[hf]) * H + rj[hf]) * H + k] : 0.f;
+      }
+      wa[i][kt] = make_a(v[0], v[1], v[2], v[3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int hf = e >> 1, b = b0 + 2 * t4 + (e & 1);
+      xok[i][e] = rok[hf] && b < a.B;
+      xp[i][e] = a.xg + (xok[i][e] ? (size_t)b * a.gsb + (size_t)(d ? T - 1 : 0) * a.gst + (size_t)d * G * H + (size_t)rg[hf] * H + rj[hf] : 0);
+    }
   }
-  const float bhn = (G == 3 && row_ok && g == 2) ? a.bhn[d * H + j] : 0.f;
-  for (int e = tid; e < 2 * NB * KP; e += blockDim.x) h_s[e] = 0.f;
+  const long long xstep = d ? -a.gst : a.gst;
+
+  // ---- cell role: (unit, sequence) items of this thread
+  float st[ITEMS];                                        // LSTM: c ; GRU: h
+  const float* gp[ITEMS];
+  float* op[ITEMS];
+  float* svp[ITEMS];
+  int hoff[ITEMS];
+  bool item[ITEMS], live[ITEMS];
+  const size_t HN = (size_t)H * NB;
+#pragma unroll
+  for (int q = 0; q < ITEMS; ++q) {
+    const int idx = tid + q * NT, jl = idx >> 3, b = idx & 7, j = crank * Hc + jl;
+    st[q] = 0.f;
+    item[q] = idx < Hc * NB;
+    live[q] = item[q] && j < H && b0 + b < a.B;
+    gp[q] = g_s + idx;
+    hoff[q] = b * KS + j;
+    op[q] = a.out + (live[q] ? (size_t)(b0 + b) * a.osb + (size_t)(d ? T - 1 : 0) * a.ost + (size_t)d * H + j : 0);
+    svp[q] = (a.saved && live[q])
+                 ? a.saved + (((size_t)(d * a.ntile + tile) * T + (d ? T - 1 : 0)) * HN + (size_t)j * NB + b) * SP
+                 : nullptr;
+  }
+  const long long ostep = d ? -a.ost : a.ost;
+  const long long sstep = (long long)(d ? -1 : 1) * (long long)HN * SP;
+  const int gplane = Hc * NB;
+
+  for (int e = tid; e < 2 * NB * KS; e += NT) h_s[e] = 0.f;
   step_barrier<CS>();
 
-  float st[ITEMS];                                        // LSTM: c ; GRU: h
+  float xa[MT][4], xb[MT][4];                             // xg of steps tt and tt + 1: loads stay in flight for two steps
+  auto load_xg = [&](float (&dst)[MT][4]) {
 #pragma unroll
-  for (int q = 0; q < ITEMS; ++q) st[q] = 0.f;
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        dst[i][e] = xok[i][e] ? __ldg(xp[i][e]) : 0.f;
+        xp[i][e] += xstep;
+      }
+  };
+  load_xg(xa);
+  if (T > 1) load_xg(xb);
 
-  const float* xrow = a.xg + (size_t)d * G * H + (size_t)g * H + j;
-  float xv[NB];
-  {
-    const int t = d ? T - 1 : 0;
+  auto step = [&](const int tt, float (&xv)[MT][4]) {
+    float acc[MT][4], acl[MT][4];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) xv[b] = (row_ok && b0 + b < a.B) ? xrow[(size_t)(b0 + b) * a.gsb + (size_t)t * a.gst] : 0.f;
-  }
-  const size_t HN = (size_t)H * NB;
-  float* sv = a.saved ? a.saved + ((size_t)(d * a.ntile + tile) * T) * S * HN : nullptr;
-
-  for (int tt = 0; tt < T; ++tt) {
-    const int t = d ? T - 1 - tt : tt;
-    float xn[NB];
-    if (tt + 1 < T) {
-      const int tn = d ? t - 1 : t + 1;
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int b = 0; b < NB; ++b)
-        xn[b] = (row_ok && b0 + b < a.B) ? xrow[(size_t)(b0 + b) * a.gsb + (size_t)tn * a.gst] : 0.f;
-    }
-    unsigned long long acc[NB];
-    const bool hn_plane = (G == 3 && g == 2);
+      for (int e = 0; e < 4; ++e) {
+        acc[i][e] = isn[i][e >> 1] ? bhn[i][e >> 1] : xv[i][e];
+        acl[i][e] = 0.f;
+      }
+    const float* hc = h_s + (tt & 1) * NB * KS + g8 * KS + t4;
 #pragma unroll
-    for (int b = 0; b < NB; ++b) acc[b] = pack2(hn_plane ? bhn : xv[b], 0.f);
-    const float* hc = h_s + (tt & 1) * NB * KP;
-    matvec<KP, NB>(w2, hc, acc);
-    if (tid < P) {
+    for (int kt = 0; kt < KT; ++kt) {
+      const FragB hb = make_b(hc[kt * 8], hc[kt * 8 + 4]);
 #pragma unroll
-      for (int b = 0; b < NB; ++b) g_s[g * Hc * NB + jl * NB + b] = sum2(acc[b]);
-      if (hn_plane) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) g_s[3 * Hc * NB + jl * NB + b] = xv[b];
+      for (int i = 0; i < MT; ++i) {
+        mma_tf32(acl[i], wa[i][kt].lo, hb.hi);
+        mma_tf32(acl[i], wa[i][kt].hi, hb.lo);
+        mma_tf32(acc[i], wa[i][kt].hi, hb.hi);
       }
     }
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        if (rowok[i][hf]) {
+          *reinterpret_cast<float2*>(gst_p[i][hf]) =
+              make_float2(acc[i][2 * hf] + acl[i][2 * hf], acc[i][2 * hf + 1] + acl[i][2 * hf + 1]);
+          if (isn[i][hf]) *reinterpret_cast<float2*>(gst_p[i][hf] + gplane) = make_float2(xv[i][2 * hf], xv[i][2 * hf + 1]);
+        }
+      }
+    if (tt + 2 < T) load_xg(xv);                          // this register set is free again: fetch step tt + 2
     __syncthreads();
-    float* hnx = h_s + ((tt + 1) & 1) * NB * KP;
+    float* hnx = h_s + ((tt + 1) & 1) * NB * KS;
 #pragma unroll
     for (int q = 0; q < ITEMS; ++q) {
-      const int idx = tid + q * P;
-      if (tid < P && idx < Hc * NB) {
-        const int jl2 = idx / NB, b = idx - jl2 * NB, j2 = crank * Hc + jl2;
-        const float p0 = g_s[idx], p1 = g_s[Hc * NB + idx], p2 = g_s[2 * Hc * NB + idx], p3 = g_s[3 * Hc * NB + idx];
-        const bool live = j2 < H && b0 + b < a.B;
+      if (item[q]) {
+        const float p0 = gp[q][0], p1 = gp[q][gplane], p2 = gp[q][2 * gplane], p3 = gp[q][3 * gplane];
         float hnew;
-        float* svp = sv ? sv + (size_t)t * S * HN + (size_t)j2 * NB + b : nullptr;
         if (G == 4) {
-          const float ig = sigmoidf_(p0), fg = sigmoidf_(p1), gg = tanhf(p2), og = sigmoidf_(p3);
+          const float ig = sigmoidf_(p0), fg = sigmoidf_(p1), gg = tanhf_(p2), og = sigmoidf_(p3);
           const float cp = st[q], c = fmaf(fg, cp, ig * gg);
           st[q] = c;
-          hnew = og * tanhf(c);
-          if (svp && j2 < H) {
-            svp[0] = ig; svp[HN] = fg; svp[2 * HN] = gg; svp[3 * HN] = og; svp[4 * HN] = c; svp[5 * HN] = cp;
+          hnew = og * tanhf_(c);
+          if (svp[q]) {
+            float2* s2 = reinterpret_cast<float2*>(svp[q]);
+            s2[0] = make_float2(ig, fg); s2[1] = make_float2(gg, og); s2[2] = make_float2(c, cp);
           }
         } else {
-          const float rg = sigmoidf_(p0), zg = sigmoidf_(p1), ng = tanhf(fmaf(rg, p2, p3));
+          const float rgt = sigmoidf_(p0), zg = sigmoidf_(p1), ng = tanhf_(fmaf(rgt, p2, p3));
           const float hp = st[q];
           hnew = fmaf(zg, hp - ng, ng);                    // (1 - z) n + z h
           st[q] = hnew;
-          if (svp && j2 < H) {
-            svp[0] = rg; svp[HN] = zg; svp[2 * HN] = ng; svp[3 * HN] = p2; svp[4 * HN] = hp;
+          if (svp[q]) {
+            float2* s2 = reinterpret_cast<float2*>(svp[q]);
+            s2[0] = make_float2(rgt, zg); s2[1] = make_float2(ng, p2); s2[2] = make_float2(hp, 0.f);
           }
         }
-        if (live) a.out[(size_t)(b0 + b) * a.osb + (size_t)t * a.ost + (size_t)d * H + j2] = hnew;
-        if (j2 < KP) st_all<CS>(hnx + b * KP + j2, hnew);
+        if (live[q]) *op[q] = hnew;
+        st_all<CS>(hnx + hoff[q], hnew);
       }
+      op[q] += ostep;
+      if (svp[q]) svp[q] += sstep;
     }
     step_barrier<CS>();
-#pragma unroll
-    for (int b = 0; b < NB; ++b) xv[b] = xn[b];
+  };
+  for (int tt = 0; tt < T; tt += 2) {
+    step(tt, xa);
+    if (tt + 1 < T) step(tt + 1, xb);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-template <int G, int KP, int NB>
-__global__ void __launch_bounds__(256, rnn_min_blocks(KP)) k_rnn_bwd(const RnnArgs a) {
-  constexpr int CS = rnn_cluster(KP);
-  constexpr int S = rnn_saved_planes(G);
-  constexpr int ITEMS = (NB + G - 1) / G;
-  constexpr int GP = 4;                                   // gradient planes in shared memory (GRU: r, z, hn, n)
+// dh_{t-1}[k][b] = sum_{g,j} W_hh[g*H + j][k] * dg[g][j][b]: output rows = units k of this CTA (MTB m-tiles), contraction
+// index kk = g*KP + j split over NPART warps per m-tile, KTP k-tiles each.
+template <int G, int KT>
+struct RnnBwdCfg {
+  using Cfg = RnnCfg<KT>;
+  static constexpr int KP = KT * 8;
+  static constexpr int HCMAX = (KT == 16) ? 32 : KP;                    // units per CTA
+  static constexpr int MTB = (HCMAX + 15) / 16;                          // 1, 2, 4, 2
+  static constexpr int NPART = Cfg::WARPS / MTB;                         // 2, 4, 2, 4
+  static constexpr int KTP = (G * KT + NPART - 1) / NPART;               // k-tiles per warp
+  static constexpr int KK = NPART * KTP * 8;                             // padded contraction length
+  static constexpr int KS = ((4 * KP > KK ? 4 * KP : KK) + 4);           // row stride of dg_s (4 planes kept)
+};
+
+template <int G, int KT>
+__global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_bwd(const RnnArgs a) {
+  using Cfg = RnnCfg<KT>;
+  using BC = RnnBwdCfg<G, KT>;
+  constexpr int CS = Cfg::CS, ITEMS = Cfg::ITEMS, WARPS = Cfg::WARPS, NT = WARPS * 32;
+  constexpr int KP = BC::KP, KS = BC::KS, KTP = BC::KTP, NPART = BC::NPART, MTB = BC::MTB;
+  constexpr int PSTRIDE = MTB * 16 * NB;
   const int H = a.H, Hc = a.Hc, T = a.T;
   const int crank = (int)cluster_rank<CS>();
   const int tile = blockIdx.x / CS, d = blockIdx.y;
-  const int P = G * Hc, tid = threadIdx.x;
-  const int g = tid / Hc, kl = tid - g * Hc, k = crank * Hc + kl;
-  const bool col_ok = tid < P && k < H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, t4 = lane & 3;
+  const int mt = warp % MTB, part = warp / MTB;
   const int b0 = tile * NB;
 
   extern __shared__ float4 sm4[];
-  float* dg_s = reinterpret_cast<float*>(sm4);            // [2][GP][NB][KP]   (every unit of the layer)
-  float* p_s = dg_s + 2 * GP * NB * KP;                   // [G][Hc*NB]       partial W_g^T dg_g of this CTA's units
+  float* dg_s = reinterpret_cast<float*>(sm4);            // [2][8][KS]: gate gradients of EVERY unit, k index g*KP + j
+  float* p_s = dg_s + 2 * NB * KS;                        // [NPART][MTB*16*8] partial products
 
-  unsigned long long w2[KP / 2];                          // column k of gate g: W_hh[g*H + jj][k]
-  {
-    const float* wc = a.whh + (size_t)(d * G + g) * H * H + k;
+  FragA wa[KTP];                                          // A[m = unit][kk] = W_hh[g*H + j][unit]
 #pragma unroll
-    for (int jj = 0; jj < KP; jj += 2)
-      w2[jj / 2] = pack2((col_ok && jj < H) ? wc[(size_t)jj * H] : 0.f, (col_ok && jj + 1 < H) ? wc[(size_t)(jj + 1) * H] : 0.f);
+  for (int kt = 0; kt < KTP; ++kt) {
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int m = mt * 16 + g8 + 8 * (e & 1), ku = crank * Hc + m;
+      const int kk = (part * KTP + kt) * 8 + t4 + 4 * (e >> 1);
+      const int g = kk / KP, j = kk - g * KP;
+      v[e] = (m < Hc && ku < H && g < G && j < H) ? a.whh[((size_t)(d * G + g) * H + j) * H + ku] : 0.f;
+    }
+    wa[kt] = make_a(v[0], v[1], v[2], v[3]);
   }
-  for (int e = tid; e < 2 * GP * NB * KP; e += blockDim.x) dg_s[e] = 0.f;
+  for (int e = tid; e < 2 * NB * KS; e += NT) dg_s[e] = 0.f;
   step_barrier<CS>();
 
-  float dhrec[ITEMS], dcs[ITEMS];
-#pragma unroll
-  for (int q = 0; q < ITEMS; ++q) dhrec[q] = 0.f, dcs[q] = 0.f;
-
+  const int tl = d ? 0 : T - 1;                           // first step of the backward sweep
   const size_t HN = (size_t)H * NB;
-  const float* sv = a.saved + ((size_t)(d * a.ntile + tile) * T) * S * HN;
   const size_t GH = (size_t)G * H;
 
-  // prefetch registers of the pointwise role: saved planes + upstream gradient of the step about to be processed
-  float sp[ITEMS][S], du[ITEMS];
-  auto fetch = [&](int t) {
+  // ---- cell role
+  float dhrec[ITEMS], dcs[ITEMS];
+  const float* svp[ITEMS];
+  const float* dop[ITEMS];
+  const float* pp[ITEMS];
+  int goff[ITEMS];
+  bool item[ITEMS], live[ITEMS];
+#pragma unroll
+  for (int q = 0; q < ITEMS; ++q) {
+    const int idx = tid + q * NT, jl = idx >> 3, b = idx & 7, j = crank * Hc + jl;
+    dhrec[q] = 0.f, dcs[q] = 0.f;
+    item[q] = idx < Hc * NB;
+    live[q] = item[q] && j < H && b0 + b < a.B;
+    goff[q] = b * KS + j;
+    pp[q] = p_s + idx;
+    svp[q] = a.saved + (live[q] ? (((size_t)(d * a.ntile + tile) * T + tl) * HN + (size_t)j * NB + b) * SP : 0);
+    dop[q] = a.dout + (live[q] ? (size_t)(b0 + b) * a.osb + (size_t)tl * a.ost + (size_t)d * H + j : 0);
+  }
+  const long long ostep = d ? a.ost : -a.ost;             // the sweep runs against the forward direction
+  const long long sstep = (long long)(d ? 1 : -1) * (long long)HN * SP;
+
+  // ---- copy role: warp w moves the (gate plane, sequence) rows w*RPW .. of dg_s to global memory, lanes over units
+  constexpr int RPW = 32 / WARPS;                         // 32 = 4 planes x 8 sequences
+  constexpr int JL = (KT == 16) ? 32 : KP;                // units per CTA, padded
+  float* cp_g[RPW];
+  int cp_s[RPW];
+  long long cp_step[RPW];
+  bool cp_ok[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = warp * RPW + r, g = row & 3, b = row >> 2;
+    cp_ok[r] = b0 + b < a.B;
+    cp_s[r] = b * KS + g * KP + crank * Hc;
+    const size_t xrow = (size_t)(b0 + b) * a.gsb + (size_t)tl * a.gst + (size_t)d * GH + (size_t)crank * Hc;
+    const size_t orow = (size_t)(b0 + b) * a.osb + (size_t)tl * a.ost + (size_t)d * H + (size_t)crank * Hc;
+    if (!cp_ok[r]) {
+      cp_g[r] = a.dxg; cp_step[r] = 0;
+    } else if (G == 4) {
+      cp_g[r] = a.dxg + xrow + (size_t)g * H; cp_step[r] = d ? a.gst : -a.gst;
+    } else if (g == 2) {                                  // GRU: d / d (W_hn h + b_hn) has its own output
+      cp_g[r] = a.dhn + orow; cp_step[r] = ostep;
+    } else {
+      cp_g[r] = a.dxg + xrow + (size_t)(g == 3 ? 2 : g) * H; cp_step[r] = d ? a.gst : -a.gst;
+    }
+  }
+
+  // prefetch registers of the cell role: saved activations + upstream gradient, two steps deep
+  float2 sa[ITEMS][3], sb[ITEMS][3];
+  float ua[ITEMS], ub[ITEMS];
+  auto fetch = [&](float2 (&sp)[ITEMS][3], float (&du)[ITEMS]) {
 #pragma unroll
     for (int q = 0; q < ITEMS; ++q) {
-      const int idx = tid + q * P;
-      const int jl2 = idx / NB, b = idx - jl2 * NB, j2 = crank * Hc + jl2;
-      const bool ok = tid < P && idx < Hc * NB && j2 < H;
-#pragma unroll
-      for (int s = 0; s < S; ++s) sp[q][s] = ok ? sv[((size_t)t * S + s) * HN + (size_t)j2 * NB + b] : 0.f;
-      du[q] = (ok && b0 + b < a.B) ? a.dout[(size_t)(b0 + b) * a.osb + (size_t)t * a.ost + (size_t)d * H + j2] : 0.f;
+      if (live[q]) {
+        const float2* s2 = reinterpret_cast<const float2*>(svp[q]);
+        sp[q][0] = __ldg(s2); sp[q][1] = __ldg(s2 + 1); sp[q][2] = __ldg(s2 + 2);
+        du[q] = __ldg(dop[q]);
+      } else {
+        sp[q][0] = sp[q][1] = sp[q][2] = make_float2(0.f, 0.f);
+        du[q] = 0.f;
+      }
+      svp[q] += sstep;
+      dop[q] += ostep;
     }
   };
-  fetch(d ? 0 : T - 1);
+  fetch(sa, ua);
+  if (T > 1) fetch(sb, ub);
 
-  for (int tt = T - 1; tt >= 0; --tt) {
-    const int t = d ? T - 1 - tt : tt;
-    float* dgc = dg_s + (tt & 1) * GP * NB * KP;
-    // ---- pointwise role: gradient of the gate pre-activations of step t
+  auto step = [&](const int n, float2 (&sp)[ITEMS][3], float (&du)[ITEMS]) {   // n-th step of the sweep
+    float* dgc = dg_s + (n & 1) * NB * KS;
+    // ---- cell role: gradient of the gate pre-activations
 #pragma unroll
     for (int q = 0; q < ITEMS; ++q) {
-      const int idx = tid + q * P;
-      if (tid < P && idx < Hc * NB) {
-        const int jl2 = idx / NB, b = idx - jl2 * NB, j2 = crank * Hc + jl2;
+      if (item[q]) {
         const float dh = du[q] + dhrec[q];
         float d0, d1, d2, d3;
         if (G == 4) {
-          const float ig = sp[q][0], fg = sp[q][1], gg = sp[q][2], og = sp[q][3], c = sp[q][4], cp = sp[q][5 % S];
-          const float tc = tanhf(c);
+          const float ig = sp[q][0].x, fg = sp[q][0].y, gg = sp[q][1].x, og = sp[q][1].y, c = sp[q][2].x, cp = sp[q][2].y;
+          const float tc = tanhf_(c);
           const float dc = fmaf(dh * og, 1.f - tc * tc, dcs[q]);
           dcs[q] = dc * fg;
           d0 = dc * gg * ig * (1.f - ig);
@@ -284,77 +405,82 @@ __global__ void __launch_bounds__(256, rnn_min_blocks(KP)) k_rnn_bwd(const RnnAr
           d3 = dh * tc * og * (1.f - og);
           dhrec[q] = 0.f;
         } else {
-          const float rg = sp[q][0], zg = sp[q][1], ng = sp[q][2], hnb = sp[q][3], hp = sp[q][4];
+          const float rgt = sp[q][0].x, zg = sp[q][0].y, ng = sp[q][1].x, hnb = sp[q][1].y, hp = sp[q][2].x;
           const float dnp = dh * (1.f - zg) * (1.f - ng * ng);
-          d0 = dnp * hnb * rg * (1.f - rg);
+          d0 = dnp * hnb * rgt * (1.f - rgt);
           d1 = dh * (hp - ng) * zg * (1.f - zg);
-          d2 = dnp * rg;                                   // d / d (W_hn h + b_hn)
-          d3 = dnp;                                        // d / d (xg n-plane)
+          d2 = dnp * rgt;                                  // d / d (W_hn h + b_hn)
+          d3 = dnp;                                        // d / d (xg n-plane); not part of the contraction
           dhrec[q] = dh * zg;                              // direct path h_{t-1} -> h_t
         }
-        if (j2 < KP) {
-          st_all<CS>(dgc + (0 * NB + b) * KP + j2, d0);
-          st_all<CS>(dgc + (1 * NB + b) * KP + j2, d1);
-          st_all<CS>(dgc + (2 * NB + b) * KP + j2, d2);
-          st_all<CS>(dgc + (3 * NB + b) * KP + j2, d3);
-        }
+        float* p = dgc + goff[q];
+        st_all<CS>(p, d0);
+        st_all<CS>(p + KP, d1);
+        st_all<CS>(p + 2 * KP, d2);
+        if (G == 4) st_all<CS>(p + 3 * KP, d3); else p[3 * KP] = d3;
       }
     }
-    if (tt > 0) fetch(d ? T - tt : tt - 1);                // loads of the next step fly during the products
+    if (n + 2 < T) fetch(sp, du);                          // registers free again: loads of step n + 2 fly for two steps
     step_barrier<CS>();
-    // ---- product role: partial_g[k][b] = sum_jj W_hh[g*H + jj][k] * dg_g[jj][b]; dgates to global memory
+    // ---- product role
     {
-      unsigned long long acc[NB];
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* dv = dgc + g8 * KS + part * KTP * 8 + t4;
 #pragma unroll
-      for (int b = 0; b < NB; ++b) acc[b] = 0ull;
-      const float* dv = dgc + (size_t)(tid < P ? g : 0) * NB * KP;
-      matvec<KP, NB>(w2, dv, acc);
-      if (tid < P) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) p_s[g * Hc * NB + kl * NB + b] = sum2(acc[b]);
+      for (int kt = 0; kt < KTP; ++kt) {
+        const FragB gb = make_b(dv[kt * 8], dv[kt * 8 + 4]);
+        mma_tf32(acl, wa[kt].lo, gb.hi);
+        mma_tf32(acl, wa[kt].hi, gb.lo);
+        mma_tf32(acc, wa[kt].hi, gb.hi);
       }
-      if (col_ok) {
+      float* pw = p_s + part * PSTRIDE + (mt * 16 + g8) * NB + 2 * t4;
+      *reinterpret_cast<float2*>(pw) = make_float2(acc[0] + acl[0], acc[1] + acl[1]);
+      *reinterpret_cast<float2*>(pw + 8 * NB) = make_float2(acc[2] + acl[2], acc[3] + acl[3]);
+    }
+    // ---- copy role: gate gradients of this CTA's units to global memory, coalesced over the unit index
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          if (b0 + b < a.B) {
-            const size_t row = (size_t)(b0 + b) * a.gsb + (size_t)t * a.gst;
-            a.dxg[row + (size_t)d * GH + (size_t)g * H + k] = dv[b * KP + k];
-            if (G == 3 && g == 2) a.dnx[row / G + (size_t)d * H + k] = dgc[(3 * NB + b) * KP + k];
-          }
-        }
+    for (int r = 0; r < RPW; ++r) {
+#pragma unroll
+      for (int jj = 0; jj < JL; jj += 32) {
+        const int jl = jj + lane;
+        if (cp_ok[r] && jl < Hc && crank * Hc + jl < H) cp_g[r][jl] = dgc[cp_s[r] + jl];
       }
+      cp_g[r] += cp_step[r];
     }
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < ITEMS; ++q) {
-      const int idx = tid + q * P;
-      if (tid < P && idx < Hc * NB) {
+      if (item[q]) {
         float s = dhrec[q];
 #pragma unroll
-        for (int gg = 0; gg < G; ++gg) s += p_s[gg * Hc * NB + idx];
+        for (int pt = 0; pt < NPART; ++pt) s += pp[q][pt * PSTRIDE];
         dhrec[q] = s;
       }
     }
-    // p_s is rewritten only after the next step's cluster / CTA barrier, dg_s is double-buffered
+    // p_s is rewritten only after the next step's barrier, dg_s is double-buffered
+  };
+  for (int n = 0; n < T; n += 2) {
+    step(n, sa, ua);
+    if (n + 1 < T) step(n + 1, sb, ub);
   }
 }
 
-template <int G, int KP, int NB>
+template <int G, int KT>
 int launch_rnn(bool backward, const RnnArgs& a, int ndir, cudaStream_t s) {
-  constexpr int CS = rnn_cluster(KP);
-  const int P = G * a.Hc;
-  const int threads = ((P + 31) / 32) * 32;
-  if (threads > 256) return set_err(STG_ERR_UNSUPPORTED, "rnn: %d gate rows per CTA exceed 256 threads", P);
-  const size_t smem = backward ? sizeof(float) * ((size_t)2 * 4 * NB * KP + (size_t)G * a.Hc * NB)
-                               : sizeof(float) * ((size_t)2 * NB * KP + (size_t)4 * a.Hc * NB);
-  auto kern = backward ? k_rnn_bwd<G, KP, NB> : k_rnn_fwd<G, KP, NB>;
+  using Cfg = RnnCfg<KT>;
+  using BC = RnnBwdCfg<G, KT>;
+  constexpr int CS = Cfg::CS;
+  if (a.Hc > BC::HCMAX) return set_err(STG_ERR_UNSUPPORTED, "rnn: %d units per CTA exceed %d", a.Hc, BC::HCMAX);
+  const size_t smem = backward ? sizeof(float) * ((size_t)2 * NB * BC::KS + (size_t)BC::NPART * BC::MTB * 16 * NB)
+                               : sizeof(float) * ((size_t)2 * NB * (KT * 8 + 4) + (size_t)4 * a.Hc * NB + 16 * NB);
+  auto kern = backward ? k_rnn_bwd<G, KT> : k_rnn_fwd<G, KT>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_cuda("rnn smem attribute");
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(a.ntile * CS), (unsigned)ndir, 1);
-  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.blockDim = dim3((unsigned)(Cfg::WARPS * 32), 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute at = {};
@@ -368,38 +494,29 @@ int launch_rnn(bool backward, const RnnArgs& a, int ndir, cudaStream_t s) {
   return check_cuda(backward ? "k_rnn_bwd" : "k_rnn_fwd");
 }
 
-template <int G, int KP>
-int dispatch_nb(bool backward, const RnnArgs& a, int ndir, int NB, cudaStream_t s) {
-  switch (NB) {
-    case 2: return launch_rnn<G, KP, 2>(backward, a, ndir, s);
-    case 5: return launch_rnn<G, KP, 5>(backward, a, ndir, s);
-    default: return launch_rnn<G, KP, 8>(backward, a, ndir, s);
-  }
-}
 template <int G>
-int dispatch_kp(bool backward, const RnnArgs& a, int ndir, int KP, int NB, cudaStream_t s) {
-  switch (KP) {
-    case 8: return dispatch_nb<G, 8>(backward, a, ndir, NB, s);
-    case 32: return dispatch_nb<G, 32>(backward, a, ndir, NB, s);
-    case 64: return dispatch_nb<G, 64>(backward, a, ndir, NB, s);
-    default: return dispatch_nb<G, 128>(backward, a, ndir, NB, s);
+int dispatch_kt(bool backward, const RnnArgs& a, int ndir, int KT, cudaStream_t s) {
+  switch (KT) {
+    case 1: return launch_rnn<G, 1>(backward, a, ndir, s);
+    case 4: return launch_rnn<G, 4>(backward, a, ndir, s);
+    case 8: return launch_rnn<G, 8>(backward, a, ndir, s);
+    default: return launch_rnn<G, 16>(backward, a, ndir, s);
   }
 }
 
-int rnn_kp(int H) { return H <= 8 ? 8 : H <= 32 ? 32 : H <= 64 ? 64 : 128; }
+int rnn_kt(int H) { return H <= 8 ? 1 : H <= 32 ? 4 : H <= 64 ? 8 : 16; }
 
-int rnn_common(int cell, int T, int B, int H, int ndir, RnnArgs* a, int* G, int* KP, int* NB) {
+int rnn_common(int cell, int T, int B, int H, int ndir, RnnArgs* a, int* G, int* KT) {
   if (cell != STG_RNN_LSTM && cell != STG_RNN_GRU) return set_err(STG_ERR_INVALID, "rnn: unknown cell %d", cell);
   if (T < 1 || B < 1 || H < 1) return set_err(STG_ERR_INVALID, "rnn: non-positive dimension");
   if (ndir != 1 && ndir != 2) return set_err(STG_ERR_INVALID, "rnn: ndir must be 1 or 2");
   if (H > 128) return set_err(STG_ERR_UNSUPPORTED, "rnn: hidden size %d > 128", H);
   *G = cell == STG_RNN_LSTM ? 4 : 3;
-  *KP = rnn_kp(H);
-  *NB = stg_rnn_batch_tile(B);
-  const int cs = *KP > 64 ? 2 : 1;
+  *KT = rnn_kt(H);
+  const int cs = *KT == 16 ? 4 : 1;
   a->T = T; a->B = B; a->H = H;
   a->Hc = (H + cs - 1) / cs;
-  a->ntile = (B + *NB - 1) / *NB;
+  a->ntile = (B + NB - 1) / NB;
   return STG_OK;
 }
 
@@ -408,13 +525,13 @@ int rnn_common(int cell, int T, int B, int H, int ndir, RnnArgs* a, int* G, int*
 
 using namespace stg;
 
-extern "C" int stg_rnn_batch_tile(int B) { return B <= 2 ? 2 : (B <= 5 ? 5 : 8); }
+extern "C" int stg_rnn_batch_tile(int B) { (void)B; return NB; }
 
 extern "C" size_t stg_rnn_saved_floats(int cell, int T, int B, int H, int ndir) {
   if (T < 1 || B < 1 || H < 1) return 0;
-  const int NB = stg_rnn_batch_tile(B);
   const size_t ntile = (size_t)(B + NB - 1) / NB;
-  return (size_t)ndir * ntile * T * (cell == STG_RNN_LSTM ? 6 : 5) * H * NB;
+  (void)cell;
+  return (size_t)ndir * ntile * T * SP * H * NB;
 }
 
 extern "C" int stg_rnn_forward(int cell, const float* xg_dev, int64_t xg_bstride, int64_t xg_tstride,
@@ -422,8 +539,8 @@ extern "C" int stg_rnn_forward(int cell, const float* xg_dev, int64_t xg_bstride
                                float* out_dev, int64_t out_bstride, int64_t out_tstride, float* saved_dev,
                                void* stream) {
   RnnArgs a = {};
-  int G, KP, NB;
-  if (int rc = rnn_common(cell, T, B, H, ndir, &a, &G, &KP, &NB)) return rc;
+  int G, KT;
+  if (int rc = rnn_common(cell, T, B, H, ndir, &a, &G, &KT)) return rc;
   if (!xg_dev || !whh_dev || !out_dev) return set_err(STG_ERR_INVALID, "rnn: null pointer");
   if (cell == STG_RNN_GRU && !bhn_dev) return set_err(STG_ERR_INVALID, "rnn: GRU needs b_hn");
   a.xg = xg_dev; a.gsb = xg_bstride; a.gst = xg_tstride;
@@ -431,22 +548,20 @@ extern "C" int stg_rnn_forward(int cell, const float* xg_dev, int64_t xg_bstride
   a.out = out_dev; a.osb = out_bstride; a.ost = out_tstride;
   a.saved = saved_dev;
   cudaStream_t s = (cudaStream_t)stream;
-  return G == 4 ? dispatch_kp<4>(false, a, ndir, KP, NB, s) : dispatch_kp<3>(false, a, ndir, KP, NB, s);
+  return G == 4 ? dispatch_kt<4>(false, a, ndir, KT, s) : dispatch_kt<3>(false, a, ndir, KT, s);
 }
 
 extern "C" int stg_rnn_backward(int cell, const float* whh_dev, const float* saved_dev, const float* dout_dev,
                                 int64_t out_bstride, int64_t out_tstride, int T, int B, int H, int ndir,
-                                float* dxg_dev, int64_t xg_bstride, int64_t xg_tstride, float* dnx_dev, void* stream) {
+                                float* dxg_dev, int64_t xg_bstride, int64_t xg_tstride, float* dhn_dev, void* stream) {
   RnnArgs a = {};
-  int G, KP, NB;
-  if (int rc = rnn_common(cell, T, B, H, ndir, &a, &G, &KP, &NB)) return rc;
+  int G, KT;
+  if (int rc = rnn_common(cell, T, B, H, ndir, &a, &G, &KT)) return rc;
   if (!whh_dev || !saved_dev || !dout_dev || !dxg_dev) return set_err(STG_ERR_INVALID, "rnn: null pointer");
-  if (cell == STG_RNN_GRU && !dnx_dev) return set_err(STG_ERR_INVALID, "rnn: GRU backward needs dnx");
-  if (cell == STG_RNN_GRU && (xg_bstride % 3 || xg_tstride % 3))
-    return set_err(STG_ERR_INVALID, "rnn: GRU xg strides must be multiples of 3 (dnx shares them / 3)");
+  if (cell == STG_RNN_GRU && !dhn_dev) return set_err(STG_ERR_INVALID, "rnn: GRU backward needs dhn");
   a.whh = whh_dev; a.saved = const_cast<float*>(saved_dev);
   a.dout = dout_dev; a.osb = out_bstride; a.ost = out_tstride;
-  a.dxg = dxg_dev; a.gsb = xg_bstride; a.gst = xg_tstride; a.dnx = dnx_dev;
+  a.dxg = dxg_dev; a.gsb = xg_bstride; a.gst = xg_tstride; a.dhn = dhn_dev;
   cudaStream_t s = (cudaStream_t)stream;
-  return G == 4 ? dispatch_kp<4>(true, a, ndir, KP, NB, s) : dispatch_kp<3>(true, a, ndir, KP, NB, s);
+  return G == 4 ? dispatch_kt<4>(true, a, ndir, KT, s) : dispatch_kt<3>(true, a, ndir, KT, s);
 }

@@ -57,14 +57,19 @@ class _Recurrence(torch.autograd.Function):
         lib = _lib.load()
         dout = dout.contiguous()
         dxg = torch.empty(B, T, ndir * GH, device=dout.device, dtype=torch.float32)
-        dnx = torch.empty(B, T, ndir * H, device=dout.device, dtype=torch.float32) if cell == CELL_GRU else None
+        dhn = torch.empty(B, T, ndir * H, device=dout.device, dtype=torch.float32) if cell == CELL_GRU else None
         with torch.cuda.device(dout.device):
             _lib.check(lib.stg_rnn_backward(cell, whh.data_ptr(), saved.data_ptr(), dout.data_ptr(), T * ndir * H,
                                             ndir * H, T, B, H, ndir, dxg.data_ptr(), T * ndir * GH, ndir * GH,
-                                            dnx.data_ptr() if dnx is not None else None, _stream()),
+                                            dhn.data_ptr() if dhn is not None else None, _stream()),
                        "stg_rnn_backward")
         # dW_hh[d] = sum_{b,t} dgates_h[b,t,d,:] (x) h_prev[b,t,d,:]  -- a GEMM against the shifted outputs
         dgh = dxg.view(B, T, ndir, GH)
+        dbhn = None
+        if cell == CELL_GRU:                                            # recurrent side of the n gate: dhn, not dn
+            dhn4 = dhn.view(B, T, ndir, H)
+            dgh = torch.cat([dgh[..., :2 * H], dhn4], dim=-1)
+            dbhn = dhn4.sum(dim=(0, 1))                                 # [ndir, H]
         o = out.view(B, T, ndir, H)
         dwhh = torch.empty_like(whh)
         for d in range(ndir):
@@ -75,12 +80,6 @@ class _Recurrence(torch.autograd.Function):
                 else:
                     hp[:, :-1] = o[:, 1:, 1]
             dwhh[d] = dgh[:, :, d].reshape(B * T, GH).t() @ hp.view(B * T, H)
-        dbhn = None
-        if cell == CELL_GRU:
-            dbhn = dgh[..., 2 * H:].sum(dim=(0, 1))                     # [ndir, H]
-            dx = dgh.clone()
-            dx[..., 2 * H:] = dnx.view(B, T, ndir, H)                   # n plane of d loss / d xg
-            dxg = dx.view(B, T, ndir * GH)
         return dxg, dwhh, dbhn, None
 
 

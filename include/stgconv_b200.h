@@ -307,9 +307,9 @@ int stg_gat_backward(const float* Wh_dev, const float* att_w_dev, const float* a
  *   out  element (b, t, dir, j)   at b*out_bstride + t*out_tstride + dir*H + j        dir 1 runs t = T-1 .. 0
  *   whh  [ndir][G*H][H] (weight_hh_l0, weight_hh_l0_reverse), bhn [ndir][H] (GRU only)
  *   saved  stg_rnn_saved_floats() floats written by a training forward, read by the backward (null: inference)
- * backward: dout (layout of out) -> dxg (layout of xg: LSTM d loss / d xg; GRU planes r, z and d / d(W_hn h + b_hn))
- * and, GRU only, dnx = d loss / d (n plane of xg), element (b, t, dir, j) at (b*xg_bstride + t*xg_tstride)/3 + dir*H + j.
- * dW_hh = sum_t dgates_t (x) h_{t-1} is a GEMM of dxg against the shifted outputs and is left to the caller.  H <= 128. */
+ * backward: dout (layout of out) -> dxg = d loss / d xg (layout of xg) and, GRU only, dhn = d loss / d (W_hn h + b_hn)
+ * (layout of out).  dW_hh = sum_t dgates_t (x) h_{t-1} (GRU: n rows from dhn) and db_hn = sum dhn are a GEMM / a
+ * reduction over those outputs and are left to the caller.  H <= 128; 8 sequences per CTA; H > 64 runs on clusters of 4. */
 enum { STG_RNN_LSTM = 0, STG_RNN_GRU = 1 };
 int stg_rnn_batch_tile(int B);
 size_t stg_rnn_saved_floats(int cell, int T, int B, int H, int ndir);
@@ -318,7 +318,7 @@ int stg_rnn_forward(int cell, const float* xg_dev, int64_t xg_bstride, int64_t x
                     int64_t out_tstride, float* saved_dev, void* stream);
 int stg_rnn_backward(int cell, const float* whh_dev, const float* saved_dev, const float* dout_dev,
                      int64_t out_bstride, int64_t out_tstride, int T, int B, int H, int ndir, float* dxg_dev,
-                     int64_t xg_bstride, int64_t xg_tstride, float* dnx_dev, void* stream);
+                     int64_t xg_bstride, int64_t xg_tstride, float* dhn_dev, void* stream);
 
 /* Evaluation metrics (utils.py:136-169, called every epoch from trainer.py:119-121): ACCUMULATES into
  * out4_dev (4 doubles, caller zeroes): [0] sum of Score_v1 terms, [1] sum of Score_v2 terms,

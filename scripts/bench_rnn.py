@@ -30,7 +30,10 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
-for cell, B, T, I, H, bi, what in CASES:
+ONLY = os.environ.get("RNN_CASES")          # e.g. "0,1": restrict (ncu captures)
+for ci, (cell, B, T, I, H, bi, what) in enumerate(CASES):
+    if ONLY and str(ci) not in ONLY.split(","):
+        continue
     x = torch.randn(B, T, I, device=dev, requires_grad=True)
     res = {}
     for tag, cls in (("cudnn", nn.LSTM if cell == "lstm" else nn.GRU), ("native", rnn.LSTM if cell == "lstm" else rnn.GRU)):

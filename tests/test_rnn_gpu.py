@@ -1,7 +1,7 @@
 """Native recurrent layer (csrc/stg_rnn.cu behind rnn.LSTM / rnn.GRU) vs torch's own nn.LSTM / nn.GRU on the CPU in
 fp32 -- the arithmetic the reference models run (models/HAGCN/Model.py:33-53, GAT_LSTM/Model.py:129-132,
 STGNN/Model.py:72, STMSGCN/Model.py:55).  Shapes are the reference call sites' (batch, sequence, input, hidden),
-including HAGCN's long-sequence / tiny-batch layout and the 120-wide layer that runs on a 2-CTA cluster."""
+including HAGCN's long-sequence / tiny-batch layout and the 120-wide layer that runs on a 4-CTA cluster."""
 import pytest
 import torch
 import torch.nn as nn
@@ -17,7 +17,7 @@ def _rel(a, b):
 # (cell, B, T, I, H, bidirectional, batch_first)
 CASES = [
     ("lstm", 5, 700, 10, 60, True, True),      # HAGCN bi_lstm1 (sequence = bs*N)
-    ("lstm", 5, 300, 60, 120, True, True),     # HAGCN bi_lstm2: cluster of 2 CTAs
+    ("lstm", 5, 300, 60, 120, True, True),     # HAGCN bi_lstm2: cluster of 4 CTAs
     ("lstm", 2, 257, 25, 60, True, True),      # HAGCN FD002 hparams (num_patch 2)
     ("lstm", 1, 64, 50, 60, True, True),       # HAGCN FD004 hparams (num_patch 1)
     ("lstm", 128, 40, 100, 30, False, True),   # GAT_LSTM layer 1
@@ -75,9 +75,9 @@ def test_drop_in_state_dict_and_guards():
 def test_rnn_argument_validation():
     from gnn_rul_benchmarking_b200 import _lib
     lib = _lib.load()
-    assert lib.stg_rnn_batch_tile(1) == 2 and lib.stg_rnn_batch_tile(5) == 5 and lib.stg_rnn_batch_tile(100) == 8
-    assert lib.stg_rnn_saved_floats(0, 10, 5, 60, 2) == 2 * 1 * 10 * 6 * 60 * 5
-    assert lib.stg_rnn_saved_floats(1, 10, 9, 8, 1) == 1 * 2 * 10 * 5 * 8 * 8
+    assert lib.stg_rnn_batch_tile(1) == 8 and lib.stg_rnn_batch_tile(100) == 8
+    assert lib.stg_rnn_saved_floats(0, 10, 5, 60, 2) == 2 * 1 * 10 * 6 * 60 * 8
+    assert lib.stg_rnn_saved_floats(1, 10, 9, 8, 1) == 1 * 2 * 10 * 6 * 8 * 8
     assert lib.stg_rnn_forward(7, None, 0, 0, None, None, 1, 1, 1, 1, None, 0, 0, None, None) == -1
     assert b"unknown cell" in lib.stg_last_error()
     assert lib.stg_rnn_forward(0, None, 0, 0, None, None, 1, 1, 200, 1, None, 0, 0, None, None) != 0
