@@ -212,6 +212,7 @@ class _ModelAlgorithm(Algorithm):
                                           weight_decay=hparams["weight_decay"])
         self.hparams = hparams
         self._graph = None
+        self._dp_group, self._dp_world, self._dp_p2p = None, 1, False
 
     def _loss(self, X, y):
         return self.mse(self.model(X), y)
@@ -220,7 +221,11 @@ class _ModelAlgorithm(Algorithm):
         loss = self._loss(X, y)
         self.optimizer.zero_grad()
         loss.backward()
-        self.optimizer.step()
+        if self._dp_world > 1 and not self._dp_p2p:
+            import torch.distributed as dist
+            self.optimizer.flat.gather_stray_grads()
+            dist.all_reduce(self.optimizer.flat.grad, op=dist.ReduceOp.SUM, group=self._dp_group)
+        self.optimizer.step()          # fused exchange: reads the peers' gradients itself
         return loss
 
     def update(self, X, y, epoch=None):
@@ -228,10 +233,85 @@ class _ModelAlgorithm(Algorithm):
             self._gX.copy_(X, non_blocking=True)
             self._gy.copy_(y.reshape(self._gy.shape), non_blocking=True)
             self._graph.replay()
-            return {"loss": self._gloss.item()}
-        return {"loss": self._eager_update(X, y).item()}
+            loss = self._gloss.item()
+        else:
+            loss = self._eager_update(X, y).item()
+        if self._dp_p2p and int(self._p2p_flags[33]) != 0:
+            raise RuntimeError("stg_allreduce_adam: a peer did not publish its gradients in time; "
+                               "the parameter update of that step was skipped on this rank")
+        return {"loss": loss}
+
+    # ------------------------------------------------------------------ flat one-kernel optimizer / data parallel
+    def use_flat_optimizer(self, X, y):
+        """Replaces torch.optim.Adam by the library's flat Adam (one launch over one buffer, flat_optim.FlatAdam;
+        same update rule).  (X, y) is a sample batch: one probe backward finds the parameters that train at all --
+        the reference keeps never-used modules (TemporalConvNet.net0 / net1, models/ST_GCN/Model.py:110-132) whose
+        parameters torch's Adam never touches either.  Moments accumulated so far are carried over."""
+        from .flat_optim import FlatAdam, FlatParams, find_used_parameters
+        if isinstance(self.optimizer, FlatAdam):
+            return self.optimizer
+        was_training = self.training
+        self.train()
+        gen_state = torch.cuda.get_rng_state(X.device) if X.is_cuda else None
+        used = find_used_parameters(self.model, lambda: self._loss(X, y))
+        if gen_state is not None:
+            torch.cuda.set_rng_state(gen_state, X.device)          # the probe must not shift the dropout stream
+        self.train(was_training)
+        old = self.optimizer
+        hp = self.hparams
+        opt = FlatAdam(FlatParams(used), lr=hp["learning_rate"], weight_decay=hp["weight_decay"])
+        with torch.no_grad():
+            for p in used:
+                st = old.state.get(p)
+                if st:
+                    opt.state[p]["exp_avg"].copy_(st["exp_avg"])
+                    opt.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
+                    opt.step_dev.fill_(int(st["step"]))
+        self.optimizer = opt
+        return opt
+
+    def attach_data_parallel(self, X, y, group=None, broadcast=True, p2p="auto"):
+        """Shard windows across ranks: parameters / buffers broadcast from rank 0, then per step ONE
+        exchange of the flat gradient buffer -- fused into the optimizer kernel over NVLink symmetric memory
+        (p2p True / "auto") or an NCCL all-reduce followed by the Adam kernel (p2p False).  BatchNorm statistics stay
+        per rank.  (X, y): sample batch for use_flat_optimizer()."""
+        import torch.distributed as dist
+        self._dp_group, self._dp_world = group, dist.get_world_size(group)
+        if broadcast:
+            with torch.no_grad():
+                for t in list(self.model.parameters()) + list(self.model.buffers()):
+                    dist.broadcast(t, 0, group=group)
+        opt = self.use_flat_optimizer(X, y)
+        opt.grad_scale = 1.0 / self._dp_world
+        self._dp_p2p = False
+        if p2p and self._dp_world > 1 and dist.get_backend(group) == "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                dev = opt.flat.param.device
+                pg = group if group is not None else dist.group.WORLD
+                gsym = symm_mem.empty(opt.flat.n, dtype=torch.float32, device=dev)
+                hg = symm_mem.rendezvous(gsym, pg)
+                flags = symm_mem.empty(64, dtype=torch.int32, device=dev)
+                flags.zero_()
+                flags[34] = 1            # epoch of the flag protocol: monotonic, never restored (stg_p2p.cu)
+                hf = symm_mem.rendezvous(flags, pg)
+                opt.flat.replace_grad_buffer(gsym)
+                torch.cuda.synchronize(dev)
+                dist.barrier(group=group)
+                opt.attach_p2p(list(hg.buffer_ptrs), list(hf.buffer_ptrs), hg.rank, hg.world_size, (gsym, flags, hg, hf))
+                self._p2p_flags = flags
+                self._dp_p2p = True
+            except Exception:
+                if p2p is True:
+                    raise
+
+    def p2p_timed_out(self) -> bool:
+        return bool(self._dp_p2p and int(self._p2p_flags[33]) != 0)
 
     def enable_cuda_graph(self, X, y):
+        from .flat_optim import FlatAdam
+        if isinstance(self.optimizer, FlatAdam):
+            return self._capture_flat(X, y)
         params = [p for p in self.model.parameters()]
         dev = params[0].device
         hp = self.hparams
@@ -277,6 +357,33 @@ class _ModelAlgorithm(Algorithm):
                 for k, v in st.items():
                     if torch.is_tensor(v):
                         v.copy_(snap_o[i][k]) if had_state else v.zero_()
+        self.train(was_training)
+        self._graph = graph
+
+    def _capture_flat(self, X, y):
+        """Capture of the update with the flat optimizer (and, data parallel, the gradient exchange) as graph nodes."""
+        opt = self.optimizer
+        dev = opt.flat.param.device
+        self._gX, self._gy = X.detach().clone(), y.detach().clone()
+        snap_o = [t.clone() for t in opt.state_tensors()]
+        snap_b = [(b, b.detach().clone()) for b in self.model.buffers()]
+        unused = [(p, p.detach().clone()) for p in self.model.parameters() if p not in opt.state]
+        was_training = self.training
+        self.train()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._eager_update(self._gX, self._gy)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._gloss = self._eager_update(self._gX, self._gy)
+        with torch.no_grad():                       # undo the warm-up steps: weights, buffers, Adam moments
+            for t, v in zip(opt.state_tensors(), snap_o):
+                t.copy_(v)
+            for t, v in snap_b + unused:
+                t.copy_(v)
         self.train(was_training)
         self._graph = graph
 

@@ -54,6 +54,17 @@ STG_DEVINL float rcp_(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f
 STG_DEVINL float sigmoidf_(float v) { return rcp_(1.f + ex2_(-1.4426950408889634f * v)); }
 STG_DEVINL float tanhf_(float v) { return fmaf(2.f, rcp_(1.f + ex2_(-2.8853900817779268f * v)), -1.f); }
 
+// Per-step B operand split: hi = value truncated to tf32 (one LOP3), lo = the exact remainder, of which the tensor core
+// reads the leading 11 bits (cvt.rna.tf32 is a 4-instruction emulation on sm_100a: 9 instructions per value with it).
+STG_DEVINL FragB make_b_trunc(float b0, float b1) {
+  FragB f;
+  f.hi[0] = __float_as_uint(b0) & 0xffffe000u;
+  f.hi[1] = __float_as_uint(b1) & 0xffffe000u;
+  f.lo[0] = __float_as_uint(b0 - __uint_as_float(f.hi[0]));
+  f.lo[1] = __float_as_uint(b1 - __uint_as_float(f.hi[1]));
+  return f;
+}
+
 template <int CS>
 STG_DEVINL unsigned cluster_rank() {
   if (CS == 1) return 0;
@@ -155,6 +166,7 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_fwd(const Rnn
   const long long xstep = d ? -a.gst : a.gst;
 
   // ---- cell role: (unit, sequence) items of this thread
+  const int Bt = min(NB, a.B - b0);                       // live sequences of this tile
   float st[ITEMS];                                        // LSTM: c ; GRU: h
   const float* gp[ITEMS];
   float* op[ITEMS];
@@ -164,11 +176,12 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_fwd(const Rnn
   const size_t HN = (size_t)H * NB;
 #pragma unroll
   for (int q = 0; q < ITEMS; ++q) {
-    const int idx = tid + q * NT, jl = idx >> 3, b = idx & 7, j = crank * Hc + jl;
+    // only the live sequences of the tile are walked (HAGCN: 5 of 8): dead ones keep h = 0 from the initial clear
+    const int idx = tid + q * NT, jl = idx / Bt, b = idx - jl * Bt, j = crank * Hc + jl;
     st[q] = 0.f;
-    item[q] = idx < Hc * NB;
-    live[q] = item[q] && j < H && b0 + b < a.B;
-    gp[q] = g_s + idx;
+    item[q] = idx < Hc * Bt;
+    live[q] = item[q] && j < H;
+    gp[q] = g_s + jl * NB + b;
     hoff[q] = b * KS + j;
     op[q] = a.out + (live[q] ? (size_t)(b0 + b) * a.osb + (size_t)(d ? T - 1 : 0) * a.ost + (size_t)d * H + j : 0);
     svp[q] = (a.saved && live[q])
@@ -196,22 +209,23 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_fwd(const Rnn
   if (T > 1) load_xg(xb);
 
   auto step = [&](const int tt, float (&xv)[MT][4]) {
-    float acc[MT][4], acl[MT][4];
+    float acc[MT][4], acl[MT][4], acm[MT][4];             // three independent MMA chains per m-tile
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         acc[i][e] = isn[i][e >> 1] ? bhn[i][e >> 1] : xv[i][e];
         acl[i][e] = 0.f;
+        acm[i][e] = 0.f;
       }
     const float* hc = h_s + (tt & 1) * NB * KS + g8 * KS + t4;
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
-      const FragB hb = make_b(hc[kt * 8], hc[kt * 8 + 4]);
+      const FragB hb = make_b_trunc(hc[kt * 8], hc[kt * 8 + 4]);
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
         mma_tf32(acl[i], wa[i][kt].lo, hb.hi);
-        mma_tf32(acl[i], wa[i][kt].hi, hb.lo);
+        mma_tf32(acm[i], wa[i][kt].hi, hb.lo);
         mma_tf32(acc[i], wa[i][kt].hi, hb.hi);
       }
     }
@@ -221,7 +235,8 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_fwd(const Rnn
       for (int hf = 0; hf < 2; ++hf) {
         if (rowok[i][hf]) {
           *reinterpret_cast<float2*>(gst_p[i][hf]) =
-              make_float2(acc[i][2 * hf] + acl[i][2 * hf], acc[i][2 * hf + 1] + acl[i][2 * hf + 1]);
+              make_float2(acc[i][2 * hf] + (acl[i][2 * hf] + acm[i][2 * hf]),
+                          acc[i][2 * hf + 1] + (acl[i][2 * hf + 1] + acm[i][2 * hf + 1]));
           if (isn[i][hf]) *reinterpret_cast<float2*>(gst_p[i][hf] + gplane) = make_float2(xv[i][2 * hf], xv[i][2 * hf + 1]);
         }
       }
@@ -320,6 +335,7 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_bwd(const Rnn
   const size_t GH = (size_t)G * H;
 
   // ---- cell role
+  const int Bt = min(NB, a.B - b0);                       // live sequences of this tile
   float dhrec[ITEMS], dcs[ITEMS];
   const float* svp[ITEMS];
   const float* dop[ITEMS];
@@ -328,12 +344,12 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_bwd(const Rnn
   bool item[ITEMS], live[ITEMS];
 #pragma unroll
   for (int q = 0; q < ITEMS; ++q) {
-    const int idx = tid + q * NT, jl = idx >> 3, b = idx & 7, j = crank * Hc + jl;
+    const int idx = tid + q * NT, jl = idx / Bt, b = idx - jl * Bt, j = crank * Hc + jl;   // live sequences only
     dhrec[q] = 0.f, dcs[q] = 0.f;
-    item[q] = idx < Hc * NB;
-    live[q] = item[q] && j < H && b0 + b < a.B;
+    item[q] = idx < Hc * Bt;
+    live[q] = item[q] && j < H;
     goff[q] = b * KS + j;
-    pp[q] = p_s + idx;
+    pp[q] = p_s + jl * NB + b;
     svp[q] = a.saved + (live[q] ? (((size_t)(d * a.ntile + tile) * T + tl) * HN + (size_t)j * NB + b) * SP : 0);
     dop[q] = a.dout + (live[q] ? (size_t)(b0 + b) * a.osb + (size_t)tl * a.ost + (size_t)d * H + j : 0);
   }
@@ -424,18 +440,18 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_bwd(const Rnn
     step_barrier<CS>();
     // ---- product role
     {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f}, acm[4] = {0.f, 0.f, 0.f, 0.f};
       const float* dv = dgc + g8 * KS + part * KTP * 8 + t4;
 #pragma unroll
       for (int kt = 0; kt < KTP; ++kt) {
-        const FragB gb = make_b(dv[kt * 8], dv[kt * 8 + 4]);
+        const FragB gb = make_b_trunc(dv[kt * 8], dv[kt * 8 + 4]);
         mma_tf32(acl, wa[kt].lo, gb.hi);
-        mma_tf32(acl, wa[kt].hi, gb.lo);
+        mma_tf32(acm, wa[kt].hi, gb.lo);
         mma_tf32(acc, wa[kt].hi, gb.hi);
       }
       float* pw = p_s + part * PSTRIDE + (mt * 16 + g8) * NB + 2 * t4;
-      *reinterpret_cast<float2*>(pw) = make_float2(acc[0] + acl[0], acc[1] + acl[1]);
-      *reinterpret_cast<float2*>(pw + 8 * NB) = make_float2(acc[2] + acl[2], acc[3] + acl[3]);
+      *reinterpret_cast<float2*>(pw) = make_float2(acc[0] + (acl[0] + acm[0]), acc[1] + (acl[1] + acm[1]));
+      *reinterpret_cast<float2*>(pw + 8 * NB) = make_float2(acc[2] + (acl[2] + acm[2]), acc[3] + (acl[3] + acm[3]));
     }
     // ---- copy role: gate gradients of this CTA's units to global memory, coalesced over the unit index
 #pragma unroll

@@ -6,7 +6,8 @@ from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
 from gnn_rul_benchmarking_b200.configs import CONFIGS, TRAIN_PARAMS
 
 dev = torch.device("cuda:0")
-for name, B in (("FD001", 256), ("FD002", 256), ("FD003", 256), ("FD004", 256), ("NCMAPSS", 256), ("S2", 256),
+ONLY = os.environ.get("BENCH_ONLY", "")        # "siblings": skip the FC_STGNN / ASTGCNN tables
+for name, B in () if ONLY == "siblings" else (("FD001", 256), ("FD002", 256), ("FD003", 256), ("FD004", 256), ("NCMAPSS", 256), ("S2", 256),
                 ("FD004", 1024), ("FD004", 4096)):
     cfg = CONFIGS[name]
     torch.manual_seed(0)
@@ -31,7 +32,7 @@ for name, B in (("FD001", 256), ("FD002", 256), ("FD003", 256), ("FD004", 256), 
 # ASTGCNN (BASELINE configs[2], N-CMAPSS shape, batch 512): native TCN / adjacency / Chebyshev aggregation
 import warnings
 from gnn_rul_benchmarking_b200.configs import ASTGCNN_CONFIGS
-for name, B in (("CMAPSS", 100), ("NCMAPSS", 512)):
+for name, B in () if ONLY == "siblings" else (("CMAPSS", 100), ("NCMAPSS", 512)):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         alg = get_algorithm_class("ASTGCNN")(ASTGCNN_CONFIGS[name], TRAIN_PARAMS, dev).to(dev)

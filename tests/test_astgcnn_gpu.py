@@ -16,7 +16,7 @@ CFG = {"astgcnn_c": dict(num_nodes=14, time_length=50, encoder_out_dim=50, outpu
 
 
 def _rel(a, b):
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+    return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-7)      # relative to the tensor's own largest entry
 
 
 def _sub(tag, grp):

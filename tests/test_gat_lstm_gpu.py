@@ -13,7 +13,7 @@ CFG = dict(num_patch=40, patch_size=64, hidden_dim=[300, 200, 100], lstm_hidden_
 
 
 def _rel(a, b):
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+    return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-7)      # relative to the tensor's own largest entry
 
 
 def _sub(tag, grp):

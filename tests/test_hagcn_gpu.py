@@ -1,5 +1,5 @@
 """HAGCN (BASELINE.json configs[4]) drop-in: native cosine adjacency + dense aggregations (GIN, SAGPool) around the
-cuDNN Bi-LSTM encoder vs the UNMODIFIED reference model (tests/golden/aux_metrics_data.npz; encoder dropouts pinned)."""
+native Bi-LSTM recurrence (stg_rnn_*) vs the UNMODIFIED reference model (tests/golden/aux_metrics_data.npz; encoder dropouts pinned)."""
 import os
 
 import numpy as np
@@ -23,7 +23,7 @@ class PinnedDropout(torch.nn.Module):
 
 
 def _rel(a, b):
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+    return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-7)      # relative to the tensor's own largest entry
 
 
 def _sub(grp):
@@ -62,6 +62,9 @@ def test_model_matches_reference():
     grads = _sub("grad")
     assert len(grads) > 30
     for k, ref in grads.items():
+        if k.endswith("rank.bias"):          # softmax over the nodes is shift invariant: this gradient is exactly 0 in
+            assert float(named[k].grad.abs().max()) < 1e-5 and float(ref.abs().max()) < 1e-5, k   # real arithmetic
+            continue
         assert _rel(named[k].grad.cpu(), ref) < 1e-3, k
 
 

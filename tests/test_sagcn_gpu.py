@@ -13,7 +13,7 @@ CFG = dict(num_patch=160, patch_size=16, gcn_hidden_dim=100, attention_hidden_di
 
 
 def _rel(a, b):
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+    return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-7)      # relative to the tensor's own largest entry
 
 
 def _sub(grp):

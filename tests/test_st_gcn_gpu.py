@@ -23,7 +23,7 @@ class PinnedDropout(torch.nn.Module):
 
 
 def _rel(a, b):
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+    return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-7)      # relative to the tensor's own largest entry
 
 
 def _sub(tag, grp):

@@ -16,7 +16,7 @@ CFG = {"stgnn_fd4": ("STGNN", dict(patch_size=50, num_patch=1, num_nodes=14, hid
 
 
 def _rel(a, b):
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+    return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-7)      # relative to the tensor's own largest entry
 
 
 def _sub(tag, grp):
