@@ -61,12 +61,13 @@ def test_model_matches_reference():
     named = dict(model.named_parameters())
     grads = _sub("grad")
     assert len(grads) > 30
+    # per tensor, relative to its own largest entry -- floored at 1e-4 of the model's largest gradient entry: several
+    # HAGCN gradients are analytically zero (biases in front of a node softmax, everything behind the 1-node pool's
+    # softmax) and hold only rounding noise (1e-8 .. 1e-6) in the reference as well
+    floor = 1e-4 * max(float(v.abs().max()) for v in grads.values())
     for k, ref in grads.items():
-        if k.startswith("gnn") and k.endswith(("rank.bias", "mlp.2.bias")):   # both feed a softmax over the nodes, which is
-            # shift invariant: these gradients are exactly 0 in
-            assert float(named[k].grad.abs().max()) < 1e-5 and float(ref.abs().max()) < 1e-5, k   # real arithmetic
-            continue
-        assert _rel(named[k].grad.cpu(), ref) < 1e-3, k
+        err = float((named[k].grad.cpu() - ref).abs().max()) / max(floor, float(ref.abs().max()))
+        assert err < 1e-3, (k, err)
 
 
 @pytest.mark.gpu
