@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   if (tid == 0) {
     mbar_init(&ctl.bar, 1);
     mbar_init(&ctl.bar_pf, 1);
+    mbar_init(&ctl.bar_w, WPT);
+    mbar_init(&ctl.bar_x, 2);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl.tmem_base)), "r"(256));
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
   for (int c = 0; c < kCP; ++c) sof[c] = 0.f;
 #pragma unroll
   for (int h = 0; h < kHP; ++h) sov[h] = dbt_acc[h] = 0.f;
-  uint32_t ph = 0, ph_pf = 0;
+  uint32_t ph = 0, ph_pf = 0, ph_w = 0, ph_x = 0;
 
   for (int tile = cta; tile < ntiles; tile += ncta) {
     const long long g = (long long)tile * WPT + wl;
@@ -267,25 +269,25 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
     STG_STAMP(5)
     __syncthreads();
     STG_STAMP(6)
-    if (tid == 0) {
+    // a tcgen05.mma costs its issuing thread 50-110 cycles however small it is (profiles/r02_tcgen05.md): the windows'
+    // products are independent accumulators, so lane 0 of warp w issues -- and commits -- the instructions of window w
+    if ((tid & 31) == 0 && (tid >> 5) < WPT) {
       tc_fence_after();
       constexpr uint32_t id_ts = idesc_tf32(16, 0, 1);      // A from TMEM (K-major by construction), B MN-major
       constexpr uint32_t id_tt = idesc_tf32(16, 1, 1);      // A MN-major (transposed), B MN-major
+      const int w2 = tid >> 5;
+      const uint32_t dF = tmem + regB + 32 * w2, dV = dF + 16;
 #pragma unroll
-      for (int w2 = 0; w2 < WPT; ++w2) {
-        const uint32_t dF = tmem + regB + 32 * w2, dV = dF + 16;
-#pragma unroll
-        for (int ks = 0; ks < WR / 8; ++ks) {
-          const uint32_t brow = ra_lo + ((w2 * WR + ks * 8) * 128 >> 4);
-          mma_ts(dF, tmem + regA + w2 * WR + ks * 8, dsc(brow, kHiMN), id_ts, ks);
-          mma_ss(dF, dsc(t1_lo + ks * 64, kHiMN), dsc(brow, kHiMN), id_tt, 1);
-          mma_ss(dV, dsc(t2_lo + ks * 64, kHiMN), dsc(brow + 4, kHiMN), id_tt, ks);
-        }
+      for (int ks = 0; ks < WR / 8; ++ks) {
+        const uint32_t brow = ra_lo + ((w2 * WR + ks * 8) * 128 >> 4);
+        mma_ts(dF, tmem + regA + w2 * WR + ks * 8, dsc(brow, kHiMN), id_ts, ks);
+        mma_ss(dF, dsc(t1_lo + ks * 64, kHiMN), dsc(brow, kHiMN), id_tt, 1);
+        mma_ss(dV, dsc(t2_lo + ks * 64, kHiMN), dsc(brow + 4, kHiMN), id_tt, ks);
       }
-      mma_commit(&ctl.bar);
+      mma_commit(&ctl.bar_w);
     }
     STG_STAMP(7)
-    mbar_wait(&ctl.bar, ph); ph ^= 1;
+    mbar_wait(&ctl.bar_w, ph_w); ph_w ^= 1;
     tc_fence_after();
     STG_STAMP(8)
     // ---- step 7: [dF | dV] rows -> MN-major records (parameter-gradient product) and K-major rows (+ residuals)
@@ -313,10 +315,9 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
     STG_STAMP(9)
     __syncthreads();
     STG_STAMP(10)
-    if (tid == 0) {
+    if (tid == 0) {                                         // dx partial: all 128 rows share [Wm ; a0 Wtheta]
       tc_fence_after();
-      constexpr uint32_t id_x = idesc_tf32(16, 0, 0);       // dx partial: all 128 rows share [Wm ; a0 Wtheta]
-      constexpr uint32_t id_g = idesc_tf32(16, 1, 1);       // G: both transposed
+      constexpr uint32_t id_x = idesc_tf32(16, 0, 0);
 #pragma unroll
       for (int ks = 0; ks < 3; ++ks) {
         mma_ss(tmem + regA, dsc(t2k_lo + ks * 256, kHiK), dsc(wc2_lo + ks * 32, kHiK), id_x, ks);
@@ -325,13 +326,17 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
           mma_ss(tmem + regA, dsc(t2l_lo + ks * 256, kHiK), dsc(wc2_lo + ks * 32, kHiK), id_x, 1);
         }
       }
+      mma_commit(&ctl.bar_x);
+    } else if (tid == 32) {                                 // parameter-gradient product G: its own accumulator, its own thread
+      tc_fence_after();
+      constexpr uint32_t id_g = idesc_tf32(16, 1, 1);       // both transposed
 #pragma unroll
       for (int ks = 0; ks < 16; ++ks)
         mma_ss(tmem + regA + 64, dsc(t1g_lo + ks * 64, kHiMN), dsc(rb_lo + ks * 64, kHiMN), id_g, ks);
-      mma_commit(&ctl.bar);
+      mma_commit(&ctl.bar_x);
     }
     STG_STAMP(11)
-    mbar_wait(&ctl.bar, ph); ph ^= 1;
+    mbar_wait(&ctl.bar_x, ph_x); ph_x ^= 1;
     tc_fence_after();
     STG_STAMP(12)
     // ---- step 9: unfolded dx partial rows, parameter-gradient accumulators

@@ -199,6 +199,8 @@ __host__ __device__ inline int saved_mp(int M) { return M + 1; }
 struct TcCtl {
   uint64_t bar;
   uint64_t bar_pf;       // backward: completion of the prefetched blocks (TMA bulk copies)
+  uint64_t bar_w;        // backward: per-window products, one committing thread per window
+  uint64_t bar_x;        // backward: dx projection and parameter-gradient product, issued by two threads
   uint32_t tmem_base;
   uint32_t pad;
 };
