@@ -70,19 +70,19 @@ __global__ void __launch_bounds__(128, 2) k_block_bwd_tc(const BlkArgs a, int nc
     float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (tid < H) {
       const int h = tid;
-      const double R = (double)a.B * Lw * M;
-      const double m = k.stats[h] / R;
-      double var = k.stats[H + h] / R - m * m;
+      const double R = (double)a.B * Lw * M, iR = inv_d(R);
+      const double m = k.stats[h] * iR;
+      double var = k.stats[H + h] * iR - m * m;
       if (var < 0.0) var = 0.0;
-      const float r1 = (float)(1.0 / sqrt(var + (double)a.eps));
+      const float r1 = (float)rsqrt_d(var + (double)a.eps);
       const float g1 = k.g1[h];
       v[0] = g1 * r1;
       v[1] = k.b1[h] - v[0] * (float)m;
       v[2] = (float)m;
       v[3] = r1;
       v[4] = g1 * r1;
-      v[5] = (float)(g1 * k.stats[2 * H + h] / R) * r1;
-      v[6] = (float)(g1 * k.stats[3 * H + h] / R) * r1;
+      v[5] = (float)(g1 * k.stats[2 * H + h] * iR) * r1;
+      v[6] = (float)(g1 * k.stats[3 * H + h] * iR) * r1;
     }
 #pragma unroll
     for (int q = 0; q < 7; ++q) cst[kCstBn1 + q * 8 + tid] = v[q];

@@ -48,6 +48,21 @@ STG_DEVINL float warp_multi_sum(float (&w)[NP]) {
   return r;
 }
 
+// ---- prologue arithmetic
+// 1 / x and 1 / sqrt(x) in double without the division / square-root sequences (40-60 dependent instructions each; every
+// CTA of every phase ran several of them back to back in its prologue, 30-50 % of a forward phase's CTA time): fp32 MUFU
+// seed + Newton steps in double, relative error < 1e-14.
+STG_DEVINL double inv_d(double x) {
+  double r = (double)__frcp_rn((float)x);
+  r = r * (2.0 - x * r);
+  return r * (2.0 - x * r);
+}
+STG_DEVINL double rsqrt_d(double x) {
+  double r = (double)rsqrtf((float)x);
+  r = r * (1.5 - 0.5 * x * r * r);
+  return r * (1.5 - 0.5 * x * r * r);
+}
+
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) ---------------------------
 STG_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

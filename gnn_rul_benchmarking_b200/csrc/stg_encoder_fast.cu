@@ -27,11 +27,12 @@ struct EncDims {
 
 STG_DEVINL void bn_coefs_f(float* dst, int n, const double* stats, double count, const float* g, const float* be,
                            float* rm, float* rv, float eps, float momentum, bool update) {
+  const double icount = inv_d(count);
   for (int c = threadIdx.x; c < n; c += blockDim.x) {
     double m, var;
     if (stats) {
-      m = stats[c] / count;
-      var = stats[n + c] / count - m * m;
+      m = stats[c] * icount;
+      var = stats[n + c] * icount - m * m;
       if (var < 0.0) var = 0.0;
       if (update) {
         const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
@@ -42,7 +43,7 @@ STG_DEVINL void bn_coefs_f(float* dst, int n, const double* stats, double count,
       m = rm[c];
       var = rv[c];
     }
-    const float r = (float)(1.0 / sqrt(var + (double)eps));
+    const float r = (float)rsqrt_d(var + (double)eps);
     const float A = g[c] * r;
     dst[c] = A;
     dst[n + c] = be[c] - A * (float)m;
@@ -221,19 +222,20 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : (D::C > 16 || D::E > 6) ? 3 
   if (PH >= 3) bn_coefs_f(cf3, C, tr ? S3 : nullptr, cnt3, a.g3, a.be3, a.rm3, a.rv3, a.eps, a.momentum, tr && first && PH == 3);
   ENC_STAMP(7)
   if (PH == 3 || PH == 8) for (int i = tid; i < T * C; i += kT) stage[i] = a.pe[i];
+  const double ic1 = inv_d(cnt1), ic2 = inv_d(cnt2), ic3 = inv_d(cnt3);
   if (PH >= 5 && PH <= 7) for (int c = tid; c < C; c += kT) {
-    q3[c] = (float)(Bq3[c] / cnt3);
-    q3[C + c] = (float)(Bq3[C + c] / cnt3);
+    q3[c] = (float)(Bq3[c] * ic3);
+    q3[C + c] = (float)(Bq3[C + c] * ic3);
     if (PH == 5 && first) { a.dbe3[c] += (float)Bq3[c]; a.dg3[c] += (float)Bq3[C + c]; }
   }
   if (PH >= 6 && PH <= 7) for (int c = tid; c < E; c += kT) {
-    q2[c] = (float)(Bq2[c] / cnt2);
-    q2[E + c] = (float)(Bq2[E + c] / cnt2);
+    q2[c] = (float)(Bq2[c] * ic2);
+    q2[E + c] = (float)(Bq2[E + c] * ic2);
     if (PH == 6 && first) { a.dbe2[c] += (float)Bq2[c]; a.dg2[c] += (float)Bq2[E + c]; }
   }
   if (PH == 7) for (int c = tid; c < EH; c += kT) {
-    q1[c] = (float)(Bq1[c] / cnt1);
-    q1[EH + c] = (float)(Bq1[EH + c] / cnt1);
+    q1[c] = (float)(Bq1[c] * ic1);
+    q1[EH + c] = (float)(Bq1[EH + c] * ic1);
     if (first) { a.dbe1[c] += (float)Bq1[c]; a.dg1[c] += (float)Bq1[EH + c]; }
   }
   if (PH == 4 && a.fin.nblk) {
@@ -241,15 +243,15 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : (D::C > 16 || D::E > 6) ? 3 
     for (int z = 0; z < a.fin.nblk; ++z) {
       float* tb = stage + z * (4 * C + T);
       const int Hz = a.fin.H[z];
-      const double Rz = (double)a.B * a.fin.L[z] * a.fin.w[z] * N;
+      const double Rz = (double)a.B * a.fin.L[z] * a.fin.w[z] * N, iRz = inv_d(Rz);
       for (int c = tid; c < C; c += kT) {
         const float r0 = a.fin.tab[z][a.fin.CP + c];
         const double sb = a.fin.stats[z][4 * Hz + c], sg = a.fin.stats[z][4 * Hz + C + c];
         const float g0 = a.fin.g0[z][c];
         tb[c] = a.fin.tab[z][c];
         tb[C + c] = r0;
-        tb[2 * C + c] = r0 * (float)(g0 * sb / Rz);
-        tb[3 * C + c] = r0 * (float)(g0 * sg / Rz);
+        tb[2 * C + c] = r0 * (float)(g0 * sb * iRz);
+        tb[3 * C + c] = r0 * (float)(g0 * sg * iRz);
         if (first) { a.fin.db0[z][c] += (float)sb; a.fin.dg0[z][c] += (float)sg; }
       }
       for (int t2 = tid; t2 < T; t2 += kT) {

@@ -38,11 +38,11 @@ STG_DEVINL void head_bn1(const HeadArgs& a, float (*c)[4][64], bool update_runni
     const int z = i >> 6, h = i & 63;
     const HeadBlk& k = a.blk[z];
     if (h >= k.H) continue;
-    const double R = (double)a.B * k.L * k.M;
-    const double m = k.stats[h] / R;
-    double var = k.stats[k.H + h] / R - m * m;
+    const double R = (double)a.B * k.L * k.M, iR = inv_d(R);
+    const double m = k.stats[h] * iR;
+    double var = k.stats[k.H + h] * iR - m * m;
     if (var < 0.0) var = 0.0;
-    const float r1 = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float r1 = (float)rsqrt_d(var + (double)a.eps);
     const float a1 = k.g1[h] * r1;
     c[z][0][h] = a1;
     c[z][1][h] = k.b1[h] - a1 * (float)m;
