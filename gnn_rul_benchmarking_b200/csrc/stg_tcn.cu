@@ -101,6 +101,118 @@ __device__ void conv_wgrad(float* accW, const float* dc, const float* src, int C
   }
 }
 
+// ---- register-blocked variants for the kernel sizes the reference uses (ASTGCNN 6, ST_GCN / ST_Conv / STAGNN 2) ----
+// The generic loops above spend ~10 instructions per multiply-add (runtime trip counts, two shared-memory loads and a
+// bounds test per term: ncu showed ASTGCNN's six k_tcn phases at 1.06 ms of its 1.35 ms step with 15 % of the warps
+// active).  Here a thread owns a strip of TB consecutive time steps of one output channel: per input channel it loads the
+// K taps and the TB + (K-1) dil input values of the strip once and issues K * TB multiply-adds from registers.
+constexpr int kTB = 10;
+
+template <int K, int DIL>
+__device__ void causal_conv_f(const float* __restrict__ W, const float* __restrict__ in, float* __restrict__ out, int C,
+                              int L, int LP) {
+  constexpr int WIN = kTB + (K - 1) * DIL;
+  const int nb = (L + kTB - 1) / kTB;
+  for (int e = threadIdx.x; e < C * nb; e += blockDim.x) {
+    const int co = e / nb, t0 = (e - co * nb) * kTB;
+    float acc[kTB];
+#pragma unroll
+    for (int u = 0; u < kTB; ++u) acc[u] = 0.f;
+    const int s0 = t0 - (K - 1) * DIL;
+    for (int ci = 0; ci < C; ++ci) {
+      const float* w = W + (co * C + ci) * K;
+      const float* row = in + ci * LP;
+      float wv[K], win[WIN];
+#pragma unroll
+      for (int j = 0; j < K; ++j) wv[j] = w[j];
+#pragma unroll
+      for (int q = 0; q < WIN; ++q) { const int s = s0 + q; win[q] = (s >= 0 && s < L) ? row[s] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < kTB; ++u)
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[u] = fmaf(wv[j], win[u + j * DIL], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kTB; ++u) if (t0 + u < L) out[co * LP + t0 + u] = acc[u];
+  }
+}
+template <int K, int DIL>
+__device__ void causal_conv_t_f(const float* __restrict__ W, const float* __restrict__ dc, float* __restrict__ din, int C,
+                                int L, int LP) {
+  constexpr int WIN = kTB + (K - 1) * DIL;
+  const int nb = (L + kTB - 1) / kTB;
+  for (int e = threadIdx.x; e < C * nb; e += blockDim.x) {
+    const int ci = e / nb, s0 = (e - ci * nb) * kTB;
+    float acc[kTB];
+#pragma unroll
+    for (int u = 0; u < kTB; ++u) acc[u] = 0.f;
+    for (int co = 0; co < C; ++co) {
+      const float* w = W + (co * C + ci) * K;
+      const float* row = dc + co * LP;
+      float wv[K], win[WIN];
+#pragma unroll
+      for (int j = 0; j < K; ++j) wv[j] = w[j];
+#pragma unroll
+      for (int q = 0; q < WIN; ++q) { const int t = s0 + q; win[q] = t < L ? row[t] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < kTB; ++u)
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[u] = fmaf(wv[j], win[u + (K - 1 - j) * DIL], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kTB; ++u) if (s0 + u < L) din[ci * LP + s0 + u] += acc[u];
+  }
+}
+// thread (co, ci) owns the K taps of one filter pair; blocks of 8 time steps from registers
+template <int K, int DIL>
+__device__ void conv_wgrad_f(float* __restrict__ accW, const float* __restrict__ dc, const float* __restrict__ src, int C,
+                             int L, int LP) {
+  constexpr int TT = 8, WIN = TT + (K - 1) * DIL;
+  for (int e = threadIdx.x; e < C * C; e += blockDim.x) {
+    const int co = e / C, ci = e - co * C;
+    const float* drow = dc + co * LP;
+    const float* srow = src + ci * LP;
+    float acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = 0.f;
+    for (int t0 = 0; t0 < L; t0 += TT) {
+      float d[TT], win[WIN];
+#pragma unroll
+      for (int u = 0; u < TT; ++u) d[u] = t0 + u < L ? drow[t0 + u] : 0.f;
+#pragma unroll
+      for (int q = 0; q < WIN; ++q) { const int s = t0 - (K - 1) * DIL + q; win[q] = (s >= 0 && s < L) ? srow[s] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < TT; ++u)
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = fmaf(d[u], win[u + j * DIL], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) accW[e * K + j] += acc[j];
+  }
+}
+// dispatch on the runtime kernel size / dilation
+__device__ void conv_any(const float* W, const float* in, float* out, int C, int L, int LP, int K, int dil) {
+  if (K == 6 && dil == 1) causal_conv_f<6, 1>(W, in, out, C, L, LP);
+  else if (K == 6 && dil == 2) causal_conv_f<6, 2>(W, in, out, C, L, LP);
+  else if (K == 2 && dil == 1) causal_conv_f<2, 1>(W, in, out, C, L, LP);
+  else if (K == 2 && dil == 2) causal_conv_f<2, 2>(W, in, out, C, L, LP);
+  else causal_conv(W, in, out, C, L, LP, K, dil);
+}
+__device__ void conv_t_any(const float* W, const float* dc, float* din, int C, int L, int LP, int K, int dil) {
+  if (K == 6 && dil == 1) causal_conv_t_f<6, 1>(W, dc, din, C, L, LP);
+  else if (K == 6 && dil == 2) causal_conv_t_f<6, 2>(W, dc, din, C, L, LP);
+  else if (K == 2 && dil == 1) causal_conv_t_f<2, 1>(W, dc, din, C, L, LP);
+  else if (K == 2 && dil == 2) causal_conv_t_f<2, 2>(W, dc, din, C, L, LP);
+  else causal_conv_t(W, dc, din, C, L, LP, K, dil);
+}
+__device__ void wgrad_any(float* accW, const float* dc, const float* src, int C, int L, int LP, int K, int dil) {
+  if (K == 6 && dil == 1) conv_wgrad_f<6, 1>(accW, dc, src, C, L, LP);
+  else if (K == 6 && dil == 2) conv_wgrad_f<6, 2>(accW, dc, src, C, L, LP);
+  else if (K == 2 && dil == 1) conv_wgrad_f<2, 1>(accW, dc, src, C, L, LP);
+  else if (K == 2 && dil == 2) conv_wgrad_f<2, 2>(accW, dc, src, C, L, LP);
+  else conv_wgrad(accW, dc, src, C, L, LP, K, dil);
+}
+
 // PH 0..2 forward phases, 3..5 backward phases
 template <int PH>
 __global__ void __launch_bounds__(kTcnThreads) k_tcn(const TcnArgs a) {
@@ -145,7 +257,7 @@ __global__ void __launch_bounds__(kTcnThreads) k_tcn(const TcnArgs a) {
     const float* xb = a.x + (size_t)b * C * L;
     for (int e = tid; e < C * L; e += nt) xin[(e / L) * LP + e % L] = xb[e];
     __syncthreads();
-    causal_conv(W1, xin, c1, C, L, LP, K, 1);
+    conv_any(W1, xin, c1, C, L, LP, K, 1);
     __syncthreads();
     if (PH == 0) {
       for (int c = tid; c < C; c += nt) {
@@ -162,7 +274,7 @@ __global__ void __launch_bounds__(kTcnThreads) k_tcn(const TcnArgs a) {
       o0[i] = fmaxf(fmaxf(fmaf(A1[c], c1[i], C1[c]), 0.f) + xin[i], 0.f);
     }
     __syncthreads();
-    causal_conv(W2, o0, c2, C, L, LP, K, 2);
+    conv_any(W2, o0, c2, C, L, LP, K, 2);
     __syncthreads();
     if (PH == 1) {
       for (int c = tid; c < C; c += nt) {
@@ -212,8 +324,8 @@ __global__ void __launch_bounds__(kTcnThreads) k_tcn(const TcnArgs a) {
       da[i] = A2[c] * (da[i] - q2[c] - (c2[i] - mu2[c]) * r2[c] * q2[C + c]);
     }
     __syncthreads();
-    if (PH == 4) conv_wgrad(aW2, da, o0, C, L, LP, K, 2);
-    causal_conv_t(W2, da, db, C, L, LP, K, 2);             // db <- d(out_0) = ds1 + conv2^T(dc2)
+    if (PH == 4) wgrad_any(aW2, da, o0, C, L, LP, K, 2);
+    conv_t_any(W2, da, db, C, L, LP, K, 2);              // db <- d(out_0) = ds1 + conv2^T(dc2)
     __syncthreads();
     // db <- ds0 = d(out_0) * [x0 + in > 0];  da <- dn1 = ds0 * [bn1(c1) > 0]
     for (int e = tid; e < C * L; e += nt) {
@@ -243,8 +355,8 @@ __global__ void __launch_bounds__(kTcnThreads) k_tcn(const TcnArgs a) {
       da[i] = A1[c] * (da[i] - q1[c] - (c1[i] - mu1[c]) * r1[c] * q1[C + c]);
     }
     __syncthreads();
-    conv_wgrad(aW1, da, xin, C, L, LP, K, 1);
-    causal_conv_t(W1, da, db, C, L, LP, K, 1);
+    wgrad_any(aW1, da, xin, C, L, LP, K, 1);
+    conv_t_any(W1, da, db, C, L, LP, K, 1);
     __syncthreads();
     float* dxb = a.dx + (size_t)b * C * L;
     for (int e = tid; e < C * L; e += nt) dxb[e] = db[(e / L) * LP + e % L];
