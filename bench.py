@@ -166,6 +166,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self._ready = threading.Event()       # set after the first sample: NVML initialisation can take 100s of ms
 
     def _run_nvml(self):
         """NVML directly (a sample every few ms: the timed region is only tens of ms long)."""
@@ -183,7 +184,8 @@ class ClockSampler:
             sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
             r = int(get_reasons(h))
             self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
-            self._stop.wait(0.005)
+            self._ready.set()
+            self._stop.wait(0.002)
 
     def _run(self):
         try:
@@ -199,11 +201,13 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
             except Exception:
                 pass
+            self._ready.set()
             self._stop.wait(0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
+        self._ready.wait(timeout=5.0)         # the loop it brackets is only tens of ms long: sample from its first step
         return self
 
     def __exit__(self, *a):
