@@ -109,42 +109,47 @@ template <> struct RnnCfg<16> { static constexpr int KT = 16, MT = 1, WARPS = 8,
 // saved activations: [dir][tile][t][unit*8 + sequence][6]  (LSTM: i f g o c c_prev; GRU: r z n hn+b h_prev -)
 constexpr int SP = 6;
 
+// Row order of the forward tiles: an m-tile of 16 rows holds the FOUR gate rows of four hidden units, arranged so that a
+// thread's two C-fragment rows (g8, g8 + 8) are gates (0, 2) of a unit on even g8 and gates (1, 3) of the same unit on odd
+// g8.  Two lane-pair shuffles then give every thread all four gate pre-activations of one (unit, sequence) cell: the cell
+// is applied straight from the MMA accumulators -- no shared-memory gate exchange, ONE barrier per step (for h).
+// GRU: gate rows (r, z, W_hn h + b_hn, xg_n) -- the fourth row has zero weights and only carries its xg term.
 template <int G, int KT>
 __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_fwd(const RnnArgs a) {
   using Cfg = RnnCfg<KT>;
-  constexpr int CS = Cfg::CS, MT = Cfg::MT, ITEMS = Cfg::ITEMS, NT = Cfg::WARPS * 32;
+  constexpr int CS = Cfg::CS, MT = Cfg::MT, NT = Cfg::WARPS * 32;
   constexpr int KP = KT * 8, KS = KP + 4;                 // h row stride: banks of (sequence, k) pairs distinct
   const int H = a.H, Hc = a.Hc, T = a.T;
   const int crank = (int)cluster_rank<CS>();
   const int tile = blockIdx.x / CS, d = blockIdx.y;
-  const int P = G * Hc, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, t4 = lane & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, t4 = lane & 3;
   const int b0 = tile * NB;
+  const bool odd = (g8 & 1) != 0;
 
   extern __shared__ float4 sm4[];
   float* h_s = reinterpret_cast<float*>(sm4);             // [2][8][KS]
-  float* g_s = h_s + 2 * NB * KS;                         // [4][Hc*8]: gate planes (GRU: r, z, hn, xn)
 
-  // ---- product role: rows of this thread's C fragments (mt, half) -> gate g, unit j; W_hh fragments, split hi / lo
   FragA wa[MT][KT];
-  float bhn[MT][2];
-  bool isn[MT][2], rowok[MT][2];
+  float cinit[MT][2];                                     // constant C init of a row (GRU: b_hn on the hn row)
+  bool useb[MT][2], xok[MT][4], live[MT];
   const float* xp[MT][4];                                 // running pointers into xg (element e: row half e>>1, sequence 2*t4 + (e&1))
-  bool xok[MT][4];
-  float* gst_p[MT][2];
+  float* op[MT];
+  float* svp[MT];
+  int hoff[MT];
+  float st[MT];                                           // LSTM: c ; GRU: h of this thread's cell
+  const size_t HN = (size_t)H * NB;
+  const int bc = 2 * t4 + (odd ? 1 : 0);                  // sequence of this thread's cell
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
-    int rg[2], rj[2];
-    bool rok[2];
+    const int ul = (warp * MT + i) * 4 + (g8 >> 1), j = crank * Hc + ul;
+    const bool uok = ul < Hc && j < H;
+    int gate[2];
+    gate[0] = odd ? 1 : 0;
+    gate[1] = odd ? 3 : 2;
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const int row = (warp * MT + i) * 16 + g8 + 8 * hf;
-      rg[hf] = row / Hc;
-      rj[hf] = crank * Hc + (row - rg[hf] * Hc);
-      rok[hf] = row < P && rj[hf] < H;
-      rowok[i][hf] = row < P;
-      isn[i][hf] = (G == 3 && rg[hf] == 2);
-      bhn[i][hf] = (isn[i][hf] && rok[hf]) ? a.bhn[d * H + rj[hf]] : 0.f;
-      gst_p[i][hf] = g_s + row * NB + 2 * t4;
+      useb[i][hf] = (G == 3 && gate[hf] == 2);
+      cinit[i][hf] = (useb[i][hf] && uok) ? a.bhn[d * H + j] : 0.f;
     }
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
@@ -152,45 +157,29 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_fwd(const Rnn
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int hf = e & 1, k = kt * 8 + t4 + 4 * (e >> 1);
-        v[e] = (rok[hf] && k < H) ? a.whh[((size_t)(d * G + rg[hf]) * H + rj[hf]) * H + k] : 0.f;
+        const bool wrow = uok && k < H && gate[hf] < G;     // GRU: the xg_n row has no recurrent weights
+        v[e] = wrow ? a.whh[((size_t)(d * G + gate[hf]) * H + j) * H + k] : 0.f;
       }
       wa[i][kt] = make_a(v[0], v[1], v[2], v[3]);
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int hf = e >> 1, b = b0 + 2 * t4 + (e & 1);
-      xok[i][e] = rok[hf] && b < a.B;
-      xp[i][e] = a.xg + (xok[i][e] ? (size_t)b * a.gsb + (size_t)(d ? T - 1 : 0) * a.gst + (size_t)d * G * H + (size_t)rg[hf] * H + rj[hf] : 0);
+      const int xrow = (G == 3 && gate[hf] == 3) ? 2 : gate[hf];      // xg plane of this row
+      xok[i][e] = uok && b < a.B && !useb[i][hf];
+      xp[i][e] = a.xg + (xok[i][e] ? (size_t)b * a.gsb + (size_t)(d ? T - 1 : 0) * a.gst + (size_t)d * G * H + (size_t)xrow * H + j : 0);
     }
-  }
-  const long long xstep = d ? -a.gst : a.gst;
-
-  // ---- cell role: (unit, sequence) items of this thread
-  const int Bt = min(NB, a.B - b0);                       // live sequences of this tile
-  float st[ITEMS];                                        // LSTM: c ; GRU: h
-  const float* gp[ITEMS];
-  float* op[ITEMS];
-  float* svp[ITEMS];
-  int hoff[ITEMS];
-  bool item[ITEMS], live[ITEMS];
-  const size_t HN = (size_t)H * NB;
-#pragma unroll
-  for (int q = 0; q < ITEMS; ++q) {
-    // only the live sequences of the tile are walked (HAGCN: 5 of 8): dead ones keep h = 0 from the initial clear
-    const int idx = tid + q * NT, jl = idx / Bt, b = idx - jl * Bt, j = crank * Hc + jl;
-    st[q] = 0.f;
-    item[q] = idx < Hc * Bt;
-    live[q] = item[q] && j < H;
-    gp[q] = g_s + jl * NB + b;
-    hoff[q] = b * KS + j;
-    op[q] = a.out + (live[q] ? (size_t)(b0 + b) * a.osb + (size_t)(d ? T - 1 : 0) * a.ost + (size_t)d * H + j : 0);
-    svp[q] = (a.saved && live[q])
-                 ? a.saved + (((size_t)(d * a.ntile + tile) * T + (d ? T - 1 : 0)) * HN + (size_t)j * NB + b) * SP
+    st[i] = 0.f;
+    live[i] = uok && b0 + bc < a.B;
+    hoff[i] = bc * KS + (uok ? j : 0);
+    op[i] = a.out + (live[i] ? (size_t)(b0 + bc) * a.osb + (size_t)(d ? T - 1 : 0) * a.ost + (size_t)d * H + j : 0);
+    svp[i] = (a.saved && live[i])
+                 ? a.saved + (((size_t)(d * a.ntile + tile) * T + (d ? T - 1 : 0)) * HN + (size_t)j * NB + bc) * SP
                  : nullptr;
   }
+  const long long xstep = d ? -a.gst : a.gst;
   const long long ostep = d ? -a.ost : a.ost;
   const long long sstep = (long long)(d ? -1 : 1) * (long long)HN * SP;
-  const int gplane = Hc * NB;
 
   for (int e = tid; e < 2 * NB * KS; e += NT) h_s[e] = 0.f;
   step_barrier<CS>();
@@ -214,7 +203,7 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_fwd(const Rnn
     for (int i = 0; i < MT; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        acc[i][e] = isn[i][e >> 1] ? bhn[i][e >> 1] : xv[i][e];
+        acc[i][e] = useb[i][e >> 1] ? cinit[i][e >> 1] : xv[i][e];
         acl[i][e] = 0.f;
         acm[i][e] = 0.f;
       }
@@ -229,49 +218,43 @@ __global__ void __launch_bounds__(RnnCfg<KT>::WARPS * 32, 1) k_rnn_fwd(const Rnn
         mma_tf32(acc[i], wa[i][kt].hi, hb.hi);
       }
     }
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        if (rowok[i][hf]) {
-          *reinterpret_cast<float2*>(gst_p[i][hf]) =
-              make_float2(acc[i][2 * hf] + (acl[i][2 * hf] + acm[i][2 * hf]),
-                          acc[i][2 * hf + 1] + (acl[i][2 * hf + 1] + acm[i][2 * hf + 1]));
-          if (isn[i][hf]) *reinterpret_cast<float2*>(gst_p[i][hf] + gplane) = make_float2(xv[i][2 * hf], xv[i][2 * hf + 1]);
-        }
-      }
     if (tt + 2 < T) load_xg(xv);                          // this register set is free again: fetch step tt + 2
-    __syncthreads();
     float* hnx = h_s + ((tt + 1) & 1) * NB * KS;
 #pragma unroll
-    for (int q = 0; q < ITEMS; ++q) {
-      if (item[q]) {
-        const float p0 = gp[q][0], p1 = gp[q][gplane], p2 = gp[q][2 * gplane], p3 = gp[q][3 * gplane];
-        float hnew;
-        if (G == 4) {
-          const float ig = sigmoidf_(p0), fg = sigmoidf_(p1), gg = tanhf_(p2), og = sigmoidf_(p3);
-          const float cp = st[q], c = fmaf(fg, cp, ig * gg);
-          st[q] = c;
-          hnew = og * tanhf_(c);
-          if (svp[q]) {
-            float2* s2 = reinterpret_cast<float2*>(svp[q]);
-            s2[0] = make_float2(ig, fg); s2[1] = make_float2(gg, og); s2[2] = make_float2(c, cp);
-          }
-        } else {
-          const float rgt = sigmoidf_(p0), zg = sigmoidf_(p1), ng = tanhf_(fmaf(rgt, p2, p3));
-          const float hp = st[q];
-          hnew = fmaf(zg, hp - ng, ng);                    // (1 - z) n + z h
-          st[q] = hnew;
-          if (svp[q]) {
-            float2* s2 = reinterpret_cast<float2*>(svp[q]);
-            s2[0] = make_float2(rgt, zg); s2[1] = make_float2(ng, p2); s2[2] = make_float2(hp, 0.f);
-          }
+    for (int i = 0; i < MT; ++i) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = acc[i][e] + (acl[i][e] + acm[i][e]);
+      // lane pair (g8 even, g8 odd) = lanes l, l ^ 4: the even lane takes sequence 2 t4, the odd lane 2 t4 + 1
+      const float r0 = __shfl_xor_sync(0xffffffffu, odd ? v[0] : v[1], 4);
+      const float r1 = __shfl_xor_sync(0xffffffffu, odd ? v[2] : v[3], 4);
+      const float p0 = odd ? r0 : v[0], p1 = odd ? v[1] : r0, p2 = odd ? r1 : v[2], p3 = odd ? v[3] : r1;
+      float hnew;
+      if (G == 4) {
+        const float ig = sigmoidf_(p0), fg = sigmoidf_(p1), gg = tanhf_(p2), og = sigmoidf_(p3);
+        const float cp = st[i], c = fmaf(fg, cp, ig * gg);
+        st[i] = c;
+        hnew = og * tanhf_(c);
+        if (svp[i]) {
+          float2* s2 = reinterpret_cast<float2*>(svp[i]);
+          s2[0] = make_float2(ig, fg); s2[1] = make_float2(gg, og); s2[2] = make_float2(c, cp);
         }
-        if (live[q]) *op[q] = hnew;
-        st_all<CS>(hnx + hoff[q], hnew);
+      } else {
+        const float rgt = sigmoidf_(p0), zg = sigmoidf_(p1), ng = tanhf_(fmaf(rgt, p2, p3));
+        const float hp = st[i];
+        hnew = fmaf(zg, hp - ng, ng);                      // (1 - z) n + z h
+        st[i] = hnew;
+        if (svp[i]) {
+          float2* s2 = reinterpret_cast<float2*>(svp[i]);
+          s2[0] = make_float2(rgt, zg); s2[1] = make_float2(ng, p2); s2[2] = make_float2(hp, 0.f);
+        }
       }
-      op[q] += ostep;
-      if (svp[q]) svp[q] += sstep;
+      if (live[i]) {
+        *op[i] = hnew;
+        st_all<CS>(hnx + hoff[i], hnew);
+      }
+      op[i] += ostep;
+      if (svp[i]) svp[i] += sstep;
     }
     step_barrier<CS>();
   };
@@ -488,7 +471,7 @@ int launch_rnn(bool backward, const RnnArgs& a, int ndir, cudaStream_t s) {
   constexpr int CS = Cfg::CS;
   if (a.Hc > BC::HCMAX) return set_err(STG_ERR_UNSUPPORTED, "rnn: %d units per CTA exceed %d", a.Hc, BC::HCMAX);
   const size_t smem = backward ? sizeof(float) * ((size_t)2 * NB * BC::KS + (size_t)BC::NPART * BC::MTB * 16 * NB)
-                               : sizeof(float) * ((size_t)2 * NB * (KT * 8 + 4) + (size_t)4 * a.Hc * NB + 16 * NB);
+                               : sizeof(float) * ((size_t)2 * NB * (KT * 8 + 4));
   auto kern = backward ? k_rnn_bwd<G, KT> : k_rnn_fwd<G, KT>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
