@@ -112,10 +112,11 @@ MODEL_SIGNATURES["stg_agg_forward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_void_p
 MODEL_SIGNATURES["stg_agg_backward"] = (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
 MODEL_SIGNATURES["stg_tcn_forward"] = (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(StgTcnParams),
-                                                 C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p])
+                                                 C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p])
 MODEL_SIGNATURES["stg_tcn_backward"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                   C.POINTER(StgTcnParams), C.POINTER(StgTcnParams), C.c_float,
-                                                  C.c_void_p, C.c_void_p, C.c_void_p])
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
 MODEL_SIGNATURES["stg_patch_stats"] = (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p])
 MODEL_SIGNATURES["stg_patch_stats11"] = (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p])
 MODEL_SIGNATURES["stg_patch_stats12"] = (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p])

@@ -48,17 +48,20 @@ class _TcnFn(torch.autograd.Function):
         K = conv1.kernel_size[0]
         out = torch.empty_like(x)
         scratch = torch.empty(8 * Cc, device=x.device, dtype=torch.float64)
+        # raw conv outputs kept between the phase kernels and for the backward (recomputed when absent)
+        saved = torch.empty(2 * B * Cc * L, device=x.device, dtype=torch.float32) if tcn.training else None
         with torch.cuda.device(x.device):
             _lib.check(_lib.load().stg_tcn_forward(x.data_ptr(), B, Cc, L, K, C.byref(p), int(tcn.training), BN_MOMENTUM,
-                                                   BN_EPS, scratch.data_ptr(), out.data_ptr(), _stream()),
+                                                   BN_EPS, scratch.data_ptr(), saved.data_ptr() if saved is not None else None,
+                                                   out.data_ptr(), _stream()),
                        "stg_tcn_forward")
-        ctx.save_for_backward(x, scratch, w1, g1, b1, w2, g2, b2)
+        ctx.save_for_backward(x, scratch, saved, w1, g1, b1, w2, g2, b2)
         ctx.tcn, ctx.K = tcn, K
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, scratch, w1, g1, b1, w2, g2, b2 = ctx.saved_tensors
+        x, scratch, saved, w1, g1, b1, w2, g2, b2 = ctx.saved_tensors
         tcn = ctx.tcn
         if not tcn.training:
             raise RuntimeError("TemporalConvNet backward is implemented for training mode (batch statistics)")
@@ -75,7 +78,9 @@ class _TcnFn(torch.autograd.Function):
         dout = dout.contiguous()
         with torch.cuda.device(x.device):
             _lib.check(_lib.load().stg_tcn_backward(x.data_ptr(), dout.data_ptr(), B, Cc, L, ctx.K, C.byref(p), C.byref(g),
-                                                    BN_EPS, scratch.data_ptr(), dx.data_ptr(), _stream()),
+                                                    BN_EPS, scratch.data_ptr(),
+                                                    saved.data_ptr() if saved is not None else None, dx.data_ptr(),
+                                                    _stream()),
                        "stg_tcn_backward")
         return (dx, None, *grads)
 

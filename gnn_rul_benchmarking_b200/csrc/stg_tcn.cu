@@ -33,6 +33,7 @@ struct TcnArgs {
   const float* dout;
   float* dx;
   float *dW1, *dW2, *dg1, *dbe1, *dg2, *dbe2;
+  float* sv;            // optional [B][2][C*L]: raw conv1 / conv2 outputs kept between the phases (null: recomputed)
 };
 
 __device__ void bn_coef(float* dst, int C, const double* stats, double cnt, const float* g, const float* be, float* rm,
@@ -257,7 +258,18 @@ __global__ void __launch_bounds__(kTcnThreads) k_tcn(const TcnArgs a) {
     const float* xb = a.x + (size_t)b * C * L;
     for (int e = tid; e < C * L; e += nt) xin[(e / L) * LP + e % L] = xb[e];
     __syncthreads();
-    conv_any(W1, xin, c1, C, L, LP, K, 1);
+    // raw conv outputs: computed once (F1: conv1, F2: conv2) and kept in `sv` for the later phases when the caller gave it
+    float* sv1 = a.sv ? a.sv + (size_t)b * 2 * C * L : nullptr;
+    float* sv2 = sv1 ? sv1 + C * L : nullptr;
+    if (sv1 && PH >= 1) {
+      for (int e = tid; e < C * L; e += nt) c1[(e / L) * LP + e % L] = sv1[e];
+    } else {
+      conv_any(W1, xin, c1, C, L, LP, K, 1);
+      if (sv1) {
+        __syncthreads();
+        for (int e = tid; e < C * L; e += nt) sv1[e] = c1[(e / L) * LP + e % L];
+      }
+    }
     __syncthreads();
     if (PH == 0) {
       for (int c = tid; c < C; c += nt) {
@@ -274,7 +286,15 @@ __global__ void __launch_bounds__(kTcnThreads) k_tcn(const TcnArgs a) {
       o0[i] = fmaxf(fmaxf(fmaf(A1[c], c1[i], C1[c]), 0.f) + xin[i], 0.f);
     }
     __syncthreads();
-    conv_any(W2, o0, c2, C, L, LP, K, 2);
+    if (sv2 && PH >= 2) {
+      for (int e = tid; e < C * L; e += nt) c2[(e / L) * LP + e % L] = sv2[e];
+    } else {
+      conv_any(W2, o0, c2, C, L, LP, K, 2);
+      if (sv2) {
+        __syncthreads();
+        for (int e = tid; e < C * L; e += nt) sv2[e] = c2[(e / L) * LP + e % L];
+      }
+    }
     __syncthreads();
     if (PH == 1) {
       for (int c = tid; c < C; c += nt) {
@@ -418,12 +438,14 @@ int fill(TcnArgs& a, const float* x, int B, int C, int L, int K, const stg_tcn_p
 using namespace stg;
 
 extern "C" int stg_tcn_forward(const float* x_dev, int B, int C, int L, int K, const stg_tcn_params* params, int training,
-                               float momentum, float eps, double* scratch_dev, float* out_dev, void* stream) {
+                               float momentum, float eps, double* scratch_dev, float* saved_dev, float* out_dev,
+                               void* stream) {
   TcnArgs a;
   int rc = fill(a, x_dev, B, C, L, K, params, training, momentum, eps, scratch_dev);
   if (rc) return rc;
   if (!out_dev) return set_err(STG_ERR_INVALID, "null out");
   a.out = out_dev;
+  a.sv = training ? saved_dev : nullptr;
   tcn_attrs();
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = tcn_smem(C, L, K);
@@ -439,7 +461,7 @@ extern "C" int stg_tcn_forward(const float* x_dev, int B, int C, int L, int K, c
 
 extern "C" int stg_tcn_backward(const float* x_dev, const float* dout_dev, int B, int C, int L, int K,
                                 const stg_tcn_params* params, const stg_tcn_params* grads, float eps,
-                                double* scratch_dev, float* dx_dev, void* stream) {
+                                double* scratch_dev, const float* saved_dev, float* dx_dev, void* stream) {
   TcnArgs a;
   int rc = fill(a, x_dev, B, C, L, K, params, 1, 0.f, eps, scratch_dev);
   if (rc) return rc;
@@ -447,6 +469,7 @@ extern "C" int stg_tcn_backward(const float* x_dev, const float* dout_dev, int B
       !grads->bn2.weight || !grads->bn2.bias)
     return set_err(STG_ERR_INVALID, "null gradient pointer");
   a.dout = dout_dev; a.dx = dx_dev;
+  a.sv = const_cast<float*>(saved_dev);
   a.dW1 = grads->conv1_w; a.dW2 = grads->conv2_w;
   a.dg1 = grads->bn1.weight; a.dbe1 = grads->bn1.bias; a.dg2 = grads->bn2.weight; a.dbe2 = grads->bn2.bias;
   tcn_attrs();

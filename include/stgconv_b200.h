@@ -264,12 +264,14 @@ typedef struct stg_tcn_params {
   float* conv2_w;   /* conv_block2.0.weight [C,C,K] */
   stg_bn bn2;       /* conv_block2.2.*      [C]     */
 } stg_tcn_params;
+/* saved_dev (optional, 2*B*C*L floats): the training forward keeps the raw outputs of both convolutions there and the
+ * later phases / the backward of the same batch read them instead of recomputing the chain (null: recompute). */
 int stg_tcn_forward(const float* x_dev, int B, int C, int L, int K, const stg_tcn_params* params, int training,
-                    float momentum, float eps, double* scratch_dev, float* out_dev, void* stream);
+                    float momentum, float eps, double* scratch_dev, float* saved_dev, float* out_dev, void* stream);
 /* grads: same struct, weight / bias pointers address gradient buffers (ACCUMULATED into). */
 int stg_tcn_backward(const float* x_dev, const float* dout_dev, int B, int C, int L, int K,
                      const stg_tcn_params* params, const stg_tcn_params* grads, float eps, double* scratch_dev,
-                     float* dx_dev, void* stream);
+                     const float* saved_dev, float* dx_dev, void* stream);
 
 /* Per-patch statistics of the bearing models' parameter-free prefix: segment_and_compute_features
  * (models/ST_GCN/Model.py:7-52).  x [R, P] -> out [R, 10] = max, min, ptp, var, std (unbiased), mean, rms,
