@@ -190,12 +190,20 @@ int adj_check(int kind, const void* a, const void* b, long long G, int N, int F,
 
 using namespace stg;
 
+// CTA size by graph size: the kernels stride their loops by blockDim.x, so tiny graphs (STMSGCN: 20 480 graphs of 2 nodes)
+// get one or two warps per graph and up to 32 graphs resident per SM instead of 256 mostly idle threads each
+static inline int graph_threads(int N, int F) {
+  const int work = N * F > N * N ? N * F : N * N;
+  int t = (work + 31) / 32 * 32;
+  return t < 32 ? 32 : (t > stg::kAdjThreads ? stg::kAdjThreads : t);
+}
+
 extern "C" int stg_adj_forward(int kind, const float* x_dev, int64_t G, int N, int F, int top_k, float* adj_dev,
                                unsigned char* mask_dev, void* stream) {
   int rc = adj_check(kind, x_dev, adj_dev, G, N, F, false);
   if (rc) return rc;
   adj_attrs();
-  k_adj_fwd<<<(unsigned)G, kAdjThreads, adj_smem(N, F, false), (cudaStream_t)stream>>>(kind, x_dev, N, F, top_k, adj_dev,
+  k_adj_fwd<<<(unsigned)G, graph_threads(N, F), adj_smem(N, F, false), (cudaStream_t)stream>>>(kind, x_dev, N, F, top_k, adj_dev,
                                                                                       mask_dev);
   return check_cuda("stg_adj_forward");
 }
@@ -206,7 +214,7 @@ extern "C" int stg_adj_backward(int kind, const float* x_dev, const float* adj_d
   if (rc) return rc;
   if (!adj_dev || !dadj_dev) return set_err(STG_ERR_INVALID, "null adjacency / gradient");
   adj_attrs();
-  k_adj_bwd<<<(unsigned)G, kAdjThreads, adj_smem(N, F, true), (cudaStream_t)stream>>>(kind, x_dev, adj_dev, dadj_dev, N, F,
+  k_adj_bwd<<<(unsigned)G, graph_threads(N, F), adj_smem(N, F, true), (cudaStream_t)stream>>>(kind, x_dev, adj_dev, dadj_dev, N, F,
                                                                                      dx_dev);
   return check_cuda("stg_adj_backward");
 }

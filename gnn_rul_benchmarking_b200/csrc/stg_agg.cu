@@ -206,11 +206,19 @@ static int agg_check(int kind, const void* x, const void* a, const void* y, long
   return STG_OK;
 }
 
+// CTA size by graph size: the kernels stride their loops by blockDim.x, so tiny graphs (STMSGCN: 20 480 graphs of 2 nodes)
+// get one or two warps per graph and up to 32 graphs resident per SM instead of 256 mostly idle threads each
+static inline int graph_threads(int N, int F) {
+  const int work = N * F > N * N ? N * F : N * N;
+  int t = (work + 31) / 32 * 32;
+  return t < 32 ? 32 : (t > stg::kAggThreads ? stg::kAggThreads : t);
+}
+
 extern "C" int stg_agg_forward(int kind, const float* x_dev, const float* adj_dev, int64_t G, int N, int F,
                                float* out_dev, void* stream) {
   int rc = agg_check(kind, x_dev, adj_dev, out_dev, G, N, F, false);
   if (rc) return rc;
-  k_agg_fwd<<<(unsigned)G, kAggThreads, agg_smem(N, F, false), (cudaStream_t)stream>>>(kind, x_dev, adj_dev, N, F, out_dev);
+  k_agg_fwd<<<(unsigned)G, graph_threads(N, F), agg_smem(N, F, false), (cudaStream_t)stream>>>(kind, x_dev, adj_dev, N, F, out_dev);
   return check_cuda("stg_agg_forward");
 }
 
@@ -219,7 +227,7 @@ extern "C" int stg_agg_backward(int kind, const float* x_dev, const float* adj_d
   int rc = agg_check(kind, x_dev, adj_dev, dout_dev, G, N, F, true);
   if (rc) return rc;
   if (!dx_dev || !dadj_dev) return set_err(STG_ERR_INVALID, "null gradient output");
-  k_agg_bwd<<<(unsigned)G, kAggThreads, agg_smem(N, F, true), (cudaStream_t)stream>>>(kind, x_dev, adj_dev, dout_dev, N, F,
+  k_agg_bwd<<<(unsigned)G, graph_threads(N, F), agg_smem(N, F, true), (cudaStream_t)stream>>>(kind, x_dev, adj_dev, dout_dev, N, F,
                                                                                      dx_dev, dadj_dev);
   return check_cuda("stg_agg_backward");
 }
