@@ -25,32 +25,6 @@ struct EncDims {
   static constexpr int EL2 = E * L2, NL1 = EH * L1;
 };
 
-STG_DEVINL void bn_coefs_f(float* dst, int n, const double* stats, double count, const float* g, const float* be,
-                           float* rm, float* rv, float eps, float momentum, bool update) {
-  const double icount = inv_d(count);
-  for (int c = threadIdx.x; c < n; c += blockDim.x) {
-    double m, var;
-    if (stats) {
-      m = stats[c] * icount;
-      var = stats[n + c] * icount - m * m;
-      if (var < 0.0) var = 0.0;
-      if (update) {
-        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-        rm[c] = (1.f - momentum) * rm[c] + momentum * (float)m;
-        rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unb;
-      }
-    } else {
-      m = rm[c];
-      var = rv[c];
-    }
-    const float r = (float)rsqrt_d(var + (double)eps);
-    const float A = g[c] * r;
-    dst[c] = A;
-    dst[n + c] = be[c] - A * (float)m;
-    dst[2 * n + c] = (float)m;
-    dst[3 * n + c] = r;
-  }
-}
 
 // swarp[warp][idx] accumulates this warp's tiles (one owner lane per slot, no atomics); the CTA reduces its warps in
 // double at the very end.  v[0..NS) are this thread's contributions to slots 0..NS-1.
@@ -217,11 +191,53 @@ __global__ void __launch_bounds__(kT, PH == 8 ? 1 : (D::C > 16 || D::E > 6) ? 3 
   for (int i = tid; i < C * EL2; i += kT) W3[i] = a.W3[i];
   for (int i = tid; i < C; i += kT) b3[i] = a.b3[i];
   const bool first = blockIdx.x == 0, tr = a.training != 0;
-  if (PH >= 1) bn_coefs_f(cf1, EH, tr ? S1 : nullptr, cnt1, a.g1, a.be1, a.rm1, a.rv1, a.eps, a.momentum, tr && first && PH == 1);
-  if (PH >= 2) bn_coefs_f(cf2, E, tr ? S2 : nullptr, cnt2, a.g2, a.be2, a.rm2, a.rv2, a.eps, a.momentum, tr && first && PH == 2);
-  if (PH >= 3) bn_coefs_f(cf3, C, tr ? S3 : nullptr, cnt3, a.g3, a.be3, a.rm3, a.rv3, a.eps, a.momentum, tr && first && PH == 3);
+  // the (up to) three BatchNorm coefficient sets in ONE pass: thread i owns one (set, channel) -- three calls in a row were
+  // three serial rounds of dependent global loads + double arithmetic in every CTA's prologue
+  {
+    constexpr int n1 = PH >= 1 ? EH : 0, n2 = PH >= 2 ? E : 0, n3 = PH >= 3 ? C : 0;
+    for (int i = tid; i < n1 + n2 + n3; i += kT) {
+      const int set = i < n1 ? 1 : (i < n1 + n2 ? 2 : 3);
+      const int c = set == 1 ? i : (set == 2 ? i - n1 : i - n1 - n2);
+      const int n = set == 1 ? EH : (set == 2 ? E : C);
+      float* dst = set == 1 ? cf1 : (set == 2 ? cf2 : cf3);
+      const double* st = set == 1 ? S1 : (set == 2 ? S2 : S3);
+      const double count = set == 1 ? cnt1 : (set == 2 ? cnt2 : cnt3);
+      const float* gg = set == 1 ? a.g1 : (set == 2 ? a.g2 : a.g3);
+      const float* bb = set == 1 ? a.be1 : (set == 2 ? a.be2 : a.be3);
+      float* rm = set == 1 ? a.rm1 : (set == 2 ? a.rm2 : a.rm3);
+      float* rv = set == 1 ? a.rv1 : (set == 2 ? a.rv2 : a.rv3);
+      const bool update = tr && first && PH == set;
+      double m, var;
+      if (tr) {
+        const double icount = inv_d(count);
+        m = st[c] * icount;
+        var = st[n + c] * icount - m * m;
+        if (var < 0.0) var = 0.0;
+        if (update) {
+          const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+          rm[c] = (1.f - a.momentum) * rm[c] + a.momentum * (float)m;
+          rv[c] = (1.f - a.momentum) * rv[c] + a.momentum * (float)unb;
+        }
+      } else {
+        m = rm[c];
+        var = rv[c];
+      }
+      const float r = (float)rsqrt_d(var + (double)a.eps);
+      const float A = gg[c] * r;
+      dst[c] = A;
+      dst[n + c] = bb[c] - A * (float)m;
+      dst[2 * n + c] = (float)m;
+      dst[3 * n + c] = r;
+    }
+  }
   ENC_STAMP(7)
-  if (PH == 3 || PH == 8) for (int i = tid; i < T * C; i += kT) stage[i] = a.pe[i];
+  if (PH == 3 || PH == 8) {                     // positional-encoding rows: one 16-byte load round when the table is aligned
+    if ((C & 3) == 0 && ((uintptr_t)a.pe & 15) == 0) {
+      for (int i = tid; i < T * C / 4; i += kT) reinterpret_cast<float4*>(stage)[i] = reinterpret_cast<const float4*>(a.pe)[i];
+    } else {
+      for (int i = tid; i < T * C; i += kT) stage[i] = a.pe[i];
+    }
+  }
   const double ic1 = inv_d(cnt1), ic2 = inv_d(cnt2), ic3 = inv_d(cnt3);
   if (PH >= 5 && PH <= 7) for (int c = tid; c < C; c += kT) {
     q3[c] = (float)(Bq3[c] * ic3);
