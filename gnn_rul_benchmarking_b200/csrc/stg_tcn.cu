@@ -224,15 +224,18 @@ __global__ void __launch_bounds__(kTcnThreads) k_tcn(const TcnArgs a) {
   float* cf1 = W2 + NW;      float* cf2 = cf1 + 4 * C;      // A, Cc, mu, r
   float* q1 = cf2 + 4 * C;   float* q2 = q1 + 2 * C;        // backward means
   float* sacc = q2 + 2 * C;  // [2C] moment partials of this CTA
-  float* aW1 = sacc + 2 * C; float* aW2 = aW1 + NW;
-  float* xin = aW2 + NW;     float* c1 = xin + PL;          float* o0 = c1 + PL;
+  // one weight-gradient accumulator, and only in the phase that produces it (B2: dW2, B3: dW1): 512 samples then fit the
+  // device in ONE wave of 4 CTAs per SM instead of 1.15 waves of 3
+  float* aW1 = sacc + 2 * C; float* aW2 = aW1;
+  float* xin = aW1 + ((PH == 4 || PH == 5) ? NW : 0);
+  float* c1 = xin + PL;      float* o0 = c1 + PL;
   float* c2 = o0 + PL;       float* da = c2 + PL;           float* db = da + PL;
   const double cnt = (double)a.B * L;
   const double* S1 = a.st;              const double* S2 = a.st + 2 * C;
   double* Q2 = a.st + 4 * C;            double* Q1 = a.st + 6 * C;
   const bool tr = a.training != 0, first = blockIdx.x == 0;
 
-  for (int i = tid; i < NW; i += nt) { W1[i] = a.W1[i]; W2[i] = a.W2[i]; aW1[i] = 0.f; aW2[i] = 0.f; }
+  for (int i = tid; i < NW; i += nt) { W1[i] = a.W1[i]; W2[i] = a.W2[i]; if (PH == 4 || PH == 5) aW1[i] = 0.f; }
   for (int i = tid; i < 2 * C; i += nt) sacc[i] = 0.f;
   if (PH >= 1) bn_coef(cf1, C, tr ? S1 : nullptr, cnt, a.g1, a.be1, a.rm1, a.rv1, a.eps, a.momentum, tr && first && PH == 1);
   if (PH >= 2) bn_coef(cf2, C, tr ? S2 : nullptr, cnt, a.g2, a.be2, a.rm2, a.rv2, a.eps, a.momentum, tr && first && PH == 2);
@@ -391,9 +394,9 @@ __global__ void __launch_bounds__(kTcnThreads) k_tcn(const TcnArgs a) {
   if (PH == 5) for (int i = tid; i < NW; i += nt) atomicAdd(&a.dW1[i], aW1[i]);
 }
 
-size_t tcn_smem(int C, int L, int K) {
+size_t tcn_smem(int C, int L, int K, bool wgrad = true) {
   const size_t NW = (size_t)C * C * K, PL = (size_t)C * (L + 1);
-  return (4 * NW + 14 * (size_t)C + 6 * PL) * 4;
+  return ((wgrad ? 3 : 2) * NW + 14 * (size_t)C + 6 * PL) * 4;
 }
 bool g_tcn_attr = false;
 void tcn_attrs() {
@@ -407,7 +410,7 @@ void tcn_attrs() {
   g_tcn_attr = true;
 }
 int tcn_grid(int B, size_t smem) {
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  int per_sm = (int)((226 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
   int g = 148 * per_sm;
@@ -448,7 +451,7 @@ extern "C" int stg_tcn_forward(const float* x_dev, int B, int C, int L, int K, c
   a.sv = training ? saved_dev : nullptr;
   tcn_attrs();
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t smem = tcn_smem(C, L, K);
+  const size_t smem = tcn_smem(C, L, K, false);
   const int grid = tcn_grid(B, smem);
   if (training) {
     cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 8 * C, s);
@@ -474,9 +477,9 @@ extern "C" int stg_tcn_backward(const float* x_dev, const float* dout_dev, int B
   a.dg1 = grads->bn1.weight; a.dbe1 = grads->bn1.bias; a.dg2 = grads->bn2.weight; a.dbe2 = grads->bn2.bias;
   tcn_attrs();
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t smem = tcn_smem(C, L, K);
+  const size_t smem = tcn_smem(C, L, K), smem3 = tcn_smem(C, L, K, false);
   const int grid = tcn_grid(B, smem);
-  k_tcn<3><<<grid, kTcnThreads, smem, s>>>(a);
+  k_tcn<3><<<tcn_grid(B, smem3), kTcnThreads, smem3, s>>>(a);
   k_tcn<4><<<grid, kTcnThreads, smem, s>>>(a);
   k_tcn<5><<<grid, kTcnThreads, smem, s>>>(a);
   return check_cuda("stg_tcn_backward");
