@@ -70,7 +70,14 @@ class _TcnFn(torch.autograd.Function):
         p, g = _lib.StgTcnParams(), _lib.StgTcnParams()
         p.conv1_w, p.conv2_w = w1.data_ptr(), w2.data_ptr()
         p.bn1, p.bn2 = _bn_struct(bn1), _bn_struct(bn2)
-        grads = [torch.zeros_like(t) for t in (w1, g1, b1, w2, g2, b2)]
+        # one zero fill for all six gradient tensors (the kernels accumulate into them)
+        srcs = (w1, g1, b1, w2, g2, b2)
+        sizes = [(t.numel() + 3) // 4 * 4 for t in srcs]
+        flat = torch.zeros(sum(sizes), device=x.device, dtype=torch.float32)
+        grads, o = [], 0
+        for t, n in zip(srcs, sizes):
+            grads.append(flat[o:o + t.numel()].view_as(t))
+            o += n
         g.conv1_w, g.conv2_w = grads[0].data_ptr(), grads[3].data_ptr()
         g.bn1.weight, g.bn1.bias = grads[1].data_ptr(), grads[2].data_ptr()
         g.bn2.weight, g.bn2.bias = grads[4].data_ptr(), grads[5].data_ptr()
