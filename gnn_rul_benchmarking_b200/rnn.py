@@ -24,6 +24,55 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _tall_gemm_t(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a^T b for a [R, M], b [R, N] with R (= batch x time, 1e4 .. 1e5) >> M, N: the library picks a kernel that walks all of
+    R in a handful of CTAs for this shape (513 us for STGNN's three such products, ncu), so R is cut into chunks that run
+    as one batched product and the partial results are added (split-K)."""
+    R = a.shape[0]
+    S = min(256, R // 256)
+    if S < 2:
+        return a.t() @ b
+    per = R // S
+    main = per * S
+    out = torch.bmm(a[:main].view(S, per, a.shape[1]).transpose(1, 2), b[:main].view(S, per, b.shape[1])).sum(0)
+    if main < R:
+        out = out + a[main:].t() @ b[main:]
+    return out
+
+
+def _col_sum(a: torch.Tensor) -> torch.Tensor:
+    """Column sums of a tall [R, M] matrix in two stages (chunks first)."""
+    R = a.shape[0]
+    S = min(1024, R // 64)
+    if S < 2:
+        return a.sum(0)
+    per = R // S
+    main = per * S
+    out = a[:main].view(S, per, a.shape[1]).sum(1).sum(0)
+    if main < R:
+        out = out + a[main:].sum(0)
+    return out
+
+
+class _InputProjection(torch.autograd.Function):
+    """xg = x W^T + b over all time steps at once (a plain GEMM); the weight / bias gradients use the split-K helpers."""
+
+    @staticmethod
+    def forward(ctx, x2, w, b):
+        ctx.save_for_backward(x2, w)
+        ctx.has_b = b is not None
+        return torch.nn.functional.linear(x2, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        dw = _tall_gemm_t(dy, x2) if ctx.needs_input_grad[1] else None
+        db = _col_sum(dy) if (ctx.has_b and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
 class _Recurrence(torch.autograd.Function):
     """xg [B, T, ndir*G*H] (batch-major), whh [ndir, G*H, H], bhn [ndir, H] (GRU) -> out [B, T, ndir*H]."""
 
@@ -63,15 +112,15 @@ class _Recurrence(torch.autograd.Function):
                                             ndir * H, T, B, H, ndir, dxg.data_ptr(), T * ndir * GH, ndir * GH,
                                             dhn.data_ptr() if dhn is not None else None, _stream()),
                        "stg_rnn_backward")
-        # dW_hh[d] = sum_{b,t} dgates_h[b,t,d,:] (x) h_prev[b,t,d,:]  -- a GEMM against the shifted outputs
-        dgh = dxg.view(B, T, ndir, GH)
-        dbhn = None
-        if cell == CELL_GRU:                                            # recurrent side of the n gate: dhn, not dn
-            dhn4 = dhn.view(B, T, ndir, H)
-            dgh = torch.cat([dgh[..., :2 * H], dhn4], dim=-1)
-            dbhn = dhn4.sum(dim=(0, 1))                                 # [ndir, H]
+        # dW_hh[d] = sum_{b,t} dgates_h[b,t,d,:] (x) h_prev[b,t,d,:]  -- a (tall, split-K) GEMM against the shifted outputs;
+        # GRU: the n rows use dhn (recurrent side of the n gate), not dn
+        dg2 = dxg.view(B * T, ndir * GH)
         o = out.view(B, T, ndir, H)
         dwhh = torch.empty_like(whh)
+        dbhn = None
+        if cell == CELL_GRU:
+            dhn2 = dhn.view(B * T, ndir * H)
+            dbhn = _col_sum(dhn2).view(ndir, H)
         for d in range(ndir):
             hp = torch.zeros(B, T, H, device=out.device, dtype=torch.float32)
             if T > 1:
@@ -79,7 +128,12 @@ class _Recurrence(torch.autograd.Function):
                     hp[:, 1:] = o[:, :-1, 0]
                 else:
                     hp[:, :-1] = o[:, 1:, 1]
-            dwhh[d] = dgh[:, :, d].reshape(B * T, GH).t() @ hp.view(B * T, H)
+            hp2 = hp.view(B * T, H)
+            if cell == CELL_GRU:
+                dwhh[d, :2 * H] = _tall_gemm_t(dg2[:, d * GH:d * GH + 2 * H], hp2)
+                dwhh[d, 2 * H:] = _tall_gemm_t(dhn2[:, d * H:(d + 1) * H], hp2)
+            else:
+                dwhh[d] = _tall_gemm_t(dg2[:, d * GH:(d + 1) * GH], hp2)
         return dxg, dwhh, dbhn, None
 
 
@@ -115,7 +169,8 @@ def _run(mod: nn.RNNBase, x: torch.Tensor, cell: int):
         x = x.transpose(0, 1)
     G = 4 if cell == CELL_LSTM else 3
     wih, whh, bias, bhn = _layer_weights(mod, G)
-    xg = torch.nn.functional.linear(x, wih, bias)                                    # plain GEMM
+    Bx, Tx, Ix = x.shape
+    xg = _InputProjection.apply(x.reshape(Bx * Tx, Ix), wih, bias).view(Bx, Tx, -1)          # plain GEMM
     out = _Recurrence.apply(xg, whh, bhn, cell)
     H = mod.hidden_size
     h_n = out[:, -1, :H].unsqueeze(0)
