@@ -71,6 +71,85 @@ def compute_adjacency_matrix(input: torch.Tensor, top_k: int) -> torch.Tensor:
     return _Adjacency.apply(input, ADJ_GAUSS2, top_k)
 
 
+# ------------------------------------------------------------------------------------------ tall-skinny weight gradients
+def tall_gemm_t(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a^T b for a [R, M], b [R, N] with R (= graphs x nodes or batch x time, 1e4 .. 1e5) >> M, N -- the shape of every
+    weight gradient of these models.  The GEMM library walks all of R in a handful of CTAs for it (ncu: 513 us for three
+    such products in one STGNN update), so R is cut into chunks that run as ONE batched product and the partial results
+    are added (split-K)."""
+    R = a.shape[0]
+    S = min(256, R // 256)
+    if S < 2:
+        return a.t() @ b
+    per = R // S
+    main = per * S
+    out = torch.bmm(a[:main].view(S, per, a.shape[1]).transpose(1, 2), b[:main].view(S, per, b.shape[1])).sum(0)
+    if main < R:
+        out = out + a[main:].t() @ b[main:]
+    return out
+
+
+def col_sum(a: torch.Tensor) -> torch.Tensor:
+    """Column sums of a tall [R, M] matrix in two stages (chunks first)."""
+    R = a.shape[0]
+    S = min(1024, R // 64)
+    if S < 2:
+        return a.sum(0)
+    per = R // S
+    main = per * S
+    out = a[:main].view(S, per, a.shape[1]).sum(1).sum(0)
+    if main < R:
+        out = out + a[main:].sum(0)
+    return out
+
+
+class _TallLinear(torch.autograd.Function):
+    """y = x W^T + b over [R, in] rows (a plain library GEMM); weight / bias gradients through the split-K helpers."""
+
+    @staticmethod
+    def forward(ctx, x2, w, b):
+        ctx.save_for_backward(x2, w)
+        ctx.has_b = b is not None
+        return torch.nn.functional.linear(x2, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        dw = tall_gemm_t(dy, x2) if ctx.needs_input_grad[1] else None
+        db = col_sum(dy) if (ctx.has_b and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def tall_linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
+    """F.linear(x, weight, bias) for x [..., in] with many leading rows."""
+    lead = x.shape[:-1]
+    return _TallLinear.apply(x.reshape(-1, x.shape[-1]), weight, bias).view(*lead, weight.shape[0])
+
+
+class _ChebProject(torch.autograd.Function):
+    """einsum("bknf,kfo->bno", T, filters) (models/ASTGCNN/Model.py:226-228); the filter gradient is a contraction over
+    bs*N rows and goes through tall_gemm_t."""
+
+    @staticmethod
+    def forward(ctx, T, filters):
+        ctx.save_for_backward(T, filters)
+        return torch.einsum("bknf,kfo->bno", T, filters)
+
+    @staticmethod
+    def backward(ctx, dout):
+        T, filters = ctx.saved_tensors
+        bs, K, N, f = T.shape
+        dout = dout.contiguous()
+        dT = torch.einsum("bno,kfo->bknf", dout, filters) if ctx.needs_input_grad[0] else None
+        dfil = None
+        if ctx.needs_input_grad[1]:
+            Tp = T.permute(0, 2, 1, 3).reshape(bs * N, K * f)                # rows (b, n), columns (k, f)
+            dfil = tall_gemm_t(Tp, dout.view(bs * N, -1)).view(K, f, -1)
+        return dT, dfil
+
+
 # ------------------------------------------------------------------------------------------ M2 / M3
 AGG_GCN, AGG_CHEB3, AGG_AX = 0, 1, 2
 
@@ -120,7 +199,7 @@ class GCNLayer(torch.nn.Module):
         self.linear = torch.nn.Linear(in_features, out_features)
 
     def forward(self, X, A):
-        return torch.nn.functional.leaky_relu(self.linear(gcn_aggregate(X, A)))
+        return torch.nn.functional.leaky_relu(tall_linear(gcn_aggregate(X, A), self.linear.weight, self.linear.bias))
 
 
 class ChebNet(torch.nn.Module):
@@ -136,7 +215,7 @@ class ChebNet(torch.nn.Module):
 
     def forward(self, x, adj_matrix):
         T = cheb_terms(x, adj_matrix)                                  # [bs, 3, N, f]
-        return torch.einsum("bknf,kfo->bno", T, self.filters)
+        return _ChebProject.apply(T, self.filters)
 
 
 def graph_matmul(A: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
@@ -156,7 +235,7 @@ class MPNN_mk(torch.nn.Module):
         self.theta = torch.nn.ModuleList([torch.nn.Linear(input_dimension, output_dimension) for _ in range(k)])
 
     def forward(self, X, A):
-        return torch.nn.functional.leaky_relu(self.theta[0](graph_matmul(A, X)))
+        return torch.nn.functional.leaky_relu(tall_linear(graph_matmul(A, X), self.theta[0].weight, self.theta[0].bias))
 
 
 def segment_and_compute_features(data: torch.Tensor) -> torch.Tensor:

@@ -16,61 +16,13 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .primitives import _TallLinear, col_sum as _col_sum, tall_gemm_t as _tall_gemm_t
 
 CELL_LSTM, CELL_GRU = 0, 1
 
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
-def _tall_gemm_t(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a^T b for a [R, M], b [R, N] with R (= batch x time, 1e4 .. 1e5) >> M, N: the library picks a kernel that walks all of
-    R in a handful of CTAs for this shape (513 us for STGNN's three such products, ncu), so R is cut into chunks that run
-    as one batched product and the partial results are added (split-K)."""
-    R = a.shape[0]
-    S = min(256, R // 256)
-    if S < 2:
-        return a.t() @ b
-    per = R // S
-    main = per * S
-    out = torch.bmm(a[:main].view(S, per, a.shape[1]).transpose(1, 2), b[:main].view(S, per, b.shape[1])).sum(0)
-    if main < R:
-        out = out + a[main:].t() @ b[main:]
-    return out
-
-
-def _col_sum(a: torch.Tensor) -> torch.Tensor:
-    """Column sums of a tall [R, M] matrix in two stages (chunks first)."""
-    R = a.shape[0]
-    S = min(1024, R // 64)
-    if S < 2:
-        return a.sum(0)
-    per = R // S
-    main = per * S
-    out = a[:main].view(S, per, a.shape[1]).sum(1).sum(0)
-    if main < R:
-        out = out + a[main:].sum(0)
-    return out
-
-
-class _InputProjection(torch.autograd.Function):
-    """xg = x W^T + b over all time steps at once (a plain GEMM); the weight / bias gradients use the split-K helpers."""
-
-    @staticmethod
-    def forward(ctx, x2, w, b):
-        ctx.save_for_backward(x2, w)
-        ctx.has_b = b is not None
-        return torch.nn.functional.linear(x2, w, b)
-
-    @staticmethod
-    def backward(ctx, dy):
-        x2, w = ctx.saved_tensors
-        dy = dy.contiguous()
-        dx = dy @ w if ctx.needs_input_grad[0] else None
-        dw = _tall_gemm_t(dy, x2) if ctx.needs_input_grad[1] else None
-        db = _col_sum(dy) if (ctx.has_b and ctx.needs_input_grad[2]) else None
-        return dx, dw, db
 
 
 class _Recurrence(torch.autograd.Function):
@@ -170,7 +122,7 @@ def _run(mod: nn.RNNBase, x: torch.Tensor, cell: int):
     G = 4 if cell == CELL_LSTM else 3
     wih, whh, bias, bhn = _layer_weights(mod, G)
     Bx, Tx, Ix = x.shape
-    xg = _InputProjection.apply(x.reshape(Bx * Tx, Ix), wih, bias).view(Bx, Tx, -1)          # plain GEMM
+    xg = _TallLinear.apply(x.reshape(Bx * Tx, Ix), wih, bias).view(Bx, Tx, -1)          # plain GEMM
     out = _Recurrence.apply(xg, whh, bhn, cell)
     H = mod.hidden_size
     h_n = out[:, -1, :H].unsqueeze(0)
