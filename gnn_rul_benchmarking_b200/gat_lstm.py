@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .primitives import extract_features, gat_attention
+from .primitives import extract_features, gat_attention, tall_linear
 from .rnn import LSTM
 
 
@@ -28,7 +28,7 @@ class GraphAttentionLayer(nn.Module):
         self.keep_mask = None          # tests pin the attention-dropout mask here ([bs, N, N] of 0/1)
 
     def forward(self, h, adj):
-        Wh = self.linear(h)
+        Wh = tall_linear(h, self.linear.weight, self.linear.bias)
         keep = None
         if self.training and self.dropout > 0:
             keep = self.keep_mask

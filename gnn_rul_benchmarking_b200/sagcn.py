@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .primitives import cosine_distance, extract_temporal_features, gcn_aggregate
+from .primitives import cosine_distance, extract_temporal_features, gcn_aggregate, tall_linear
 
 
 def generate_cumulative_features(signals):
@@ -57,7 +57,7 @@ class GCNLayer(nn.Module):
         self.linear = nn.Linear(in_features, out_features)
 
     def forward(self, X, A):
-        return F.relu(self.linear(gcn_aggregate(X, A)))
+        return F.relu(tall_linear(gcn_aggregate(X, A), self.linear.weight, self.linear.bias))
 
 
 class GraphProjectionLayer(nn.Module):
@@ -69,7 +69,8 @@ class GraphProjectionLayer(nn.Module):
         self.project_matrices = nn.Linear(num_nodes, num_nodes)
 
     def forward(self, x):
-        return F.relu(self.linear(self.project_matrices(x.transpose(-1, -2)).transpose(-1, -2)))
+        p = tall_linear(x.transpose(-1, -2), self.project_matrices.weight, self.project_matrices.bias)
+        return F.relu(tall_linear(p.transpose(-1, -2), self.linear.weight, self.linear.bias))
 
 
 class SelfAttentionLayer(nn.Module):
@@ -81,8 +82,8 @@ class SelfAttentionLayer(nn.Module):
         self.softmax_layer = nn.Linear(attention_hidden_dim, num_nodes)
 
     def forward(self, x):
-        scores = torch.tanh(self.tanh_layer(x.transpose(-1, -2)))
-        return F.softmax(self.softmax_layer(scores), dim=-1).transpose(-1, -2)
+        scores = torch.tanh(tall_linear(x.transpose(-1, -2), self.tanh_layer.weight, self.tanh_layer.bias))
+        return F.softmax(tall_linear(scores, self.softmax_layer.weight, self.softmax_layer.bias), dim=-1).transpose(-1, -2)
 
 
 class SAGCN_model(nn.Module):
