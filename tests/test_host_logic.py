@@ -126,3 +126,57 @@ def test_sibling_algorithms_are_registered_with_reference_names():
     from gnn_rul_benchmarking_b200.algorithms import get_algorithm_class
     for name in ("FC_STGNN", "ASTGCNN", "ST_GCN", "STGNN", "STMSGCN", "GAT_LSTM", "HAGCN", "SAGCN"):
         assert get_algorithm_class(name).__name__ == name
+
+
+def test_tall_weight_gradient_helpers_match_autograd():
+    """primitives.tall_gemm_t / col_sum / tall_linear / _ChebProject (split-K weight gradients of the sibling models'
+    projections, pure torch: same numbers as the plain autograd formulas, any row count incl. ragged tails)."""
+    import torch
+    from gnn_rul_benchmarking_b200 import primitives as P
+    g = torch.Generator().manual_seed(0)
+    for R in (7, 300, 70003):
+        a, b = torch.randn(R, 24, generator=g)[:, 3:19], torch.randn(R, 8, generator=g)      # strided columns
+        ref = a.double().t() @ b.double()
+        assert float((P.tall_gemm_t(a, b).double() - ref).abs().max()) <= 2e-6 * float(ref.abs().max()) + 1e-6
+        assert float((P.col_sum(a).double() - a.double().sum(0)).abs().max()) <= 2e-6 * R ** 0.5 + 1e-6
+    x = torch.randn(40, 80, 5, generator=g, requires_grad=True)
+    w = torch.randn(7, 5, generator=g, requires_grad=True)
+    bias = torch.randn(7, generator=g, requires_grad=True)
+    y = P.tall_linear(x, w, bias)
+    assert y.shape == (40, 80, 7)
+    y.square().sum().backward()
+    got = [t.grad.clone() for t in (x, w, bias)]
+    for t in (x, w, bias):
+        t.grad = None
+    torch.nn.functional.linear(x, w, bias).square().sum().backward()
+    for a_, t in zip(got, (x, w, bias)):
+        assert float((a_ - t.grad).abs().max()) <= 1e-5 * float(t.grad.abs().max())
+    T = torch.randn(300, 3, 20, 6, generator=g, requires_grad=True)
+    F = torch.randn(3, 6, 4, generator=g, requires_grad=True)
+    P._ChebProject.apply(T, F).square().sum().backward()
+    got = (T.grad.clone(), F.grad.clone())
+    T.grad = F.grad = None
+    torch.einsum("bknf,kfo->bno", T, F).square().sum().backward()
+    assert float((got[0] - T.grad).abs().max()) <= 1e-5 * float(T.grad.abs().max())
+    assert float((got[1] - F.grad).abs().max()) <= 1e-5 * float(F.grad.abs().max())
+
+
+def test_rnn_weight_packing_matches_torch_layout():
+    """rnn._layer_weights: what the recurrence kernel receives -- stacked W_hh per direction, b_ih + b_hh folded into the
+    input projection (GRU: b_hn kept apart because it sits inside r * (W_hn h + b_hn))."""
+    import torch
+    from gnn_rul_benchmarking_b200 import rnn
+    torch.manual_seed(1)
+    m = rnn.LSTM(5, 6, batch_first=True, bidirectional=True)
+    wih, whh, bias, bhn = rnn._layer_weights(m, 4)
+    assert wih.shape == (48, 5) and whh.shape == (2, 24, 6) and bias.shape == (48,) and bhn is None
+    assert torch.equal(whh[1], m.weight_hh_l0_reverse) and torch.equal(wih[24:], m.weight_ih_l0_reverse)
+    assert torch.allclose(bias[:24], m.bias_ih_l0 + m.bias_hh_l0)
+    g = rnn.GRU(4, 3, batch_first=True)
+    wih, whh, bias, bhn = rnn._layer_weights(g, 3)
+    assert whh.shape == (1, 9, 3) and bhn.shape == (1, 3)
+    assert torch.allclose(bias[:6], g.bias_ih_l0[:6] + g.bias_hh_l0[:6])
+    assert torch.allclose(bias[6:], g.bias_ih_l0[6:]) and torch.allclose(bhn[0], g.bias_hh_l0[6:])
+    nb = rnn.GRU(4, 3, batch_first=True, bias=False)
+    _, _, bias, bhn = rnn._layer_weights(nb, 3)
+    assert bias is None and float(bhn.abs().sum()) == 0.0
