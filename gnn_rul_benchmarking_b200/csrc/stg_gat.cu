@@ -24,6 +24,31 @@ struct GatArgs {
 };
 
 // s, t, P (softmax, before dropout / adjacency), zpos (z > 0 flags) and Pd into shared memory
+// Non-zero lists of the mask adj * keep (path graphs: 3 entries per row of 40): nzr[i][.] = columns of row i, nzc[j][.] = rows
+// of column j, counts in cnt[0..N) / cnt[N..2N).  One warp per row / column, ballot + prefix popcount.
+__device__ void gat_lists(const GatArgs& a, size_t g, unsigned char* nzr, unsigned char* nzc, int* cnt) {
+  const int N = a.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* adj = a.adj + (a.adj_per_graph ? g * N * N : 0);
+  const float* keep = a.keep ? a.keep + g * N * N : nullptr;
+  for (int r = warp; r < 2 * N; r += kGatWarps) {
+    const bool col = r >= N;
+    const int i = col ? r - N : r;
+    int n = 0;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int j = j0 + lane;
+      bool nz = false;
+      if (j < N) {
+        const int e = col ? j * N + i : i * N + j;
+        nz = adj[e] != 0.f && (!keep || keep[e] != 0.f);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, nz);
+      if (nz) (col ? nzc : nzr)[i * N + n + __popc(m & ((1u << lane) - 1))] = (unsigned char)j;
+      n += __popc(m);
+    }
+    if (lane == 0) cnt[r] = n;
+  }
+}
+
 __device__ void gat_scores(const GatArgs& a, size_t g, const float* whs, int FP, float* s, float* t, float* P, float* Pd,
                            unsigned char* zpos) {
   const int N = a.N, F = a.F, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NP = N + 1;
@@ -79,18 +104,22 @@ __global__ void __launch_bounds__(kGatThreads) k_gat_fwd(const GatArgs a) {
   float* P = t + N;                      // [N][NP]
   float* Pd = P + N * NP;                // [N][NP]
   unsigned char* zpos = reinterpret_cast<unsigned char*>(Pd + N * NP);
+  unsigned char* nzr = zpos + N * N;
+  unsigned char* nzc = nzr + N * N;
+  int* cnt = reinterpret_cast<int*>(zpos + ((3 * N * N + 3) & ~3));
   const size_t g = blockIdx.x;
   const float* Wg = a.Wh + g * N * F;
   for (int e = tid; e < N * F; e += kGatThreads) whs[(e / F) * FP + e % F] = Wg[e];
+  gat_lists(a, g, nzr, nzc, cnt);
   __syncthreads();
   gat_scores(a, g, whs, FP, s, t, P, Pd, zpos);
   float* yg = a.y + g * N * F;
   for (int e = tid; e < N * F; e += kGatThreads) {
     const int i = e / F, f = e - i * F;
     float acc = 0.f;
-    for (int j = 0; j < N; ++j) {
-      const float p = Pd[i * NP + j];
-      if (p != 0.f) acc = fmaf(p, whs[j * FP + f], acc);      // path graphs: 3 non-zeros per row
+    for (int q = 0; q < cnt[i]; ++q) {                          // path graphs: 3 non-zeros per row
+      const int j = nzr[i * N + q];
+      acc = fmaf(Pd[i * NP + j], whs[j * FP + f], acc);
     }
     yg[e] = acc > 0.f ? acc : a.slope * acc;
   }
@@ -111,6 +140,9 @@ __global__ void __launch_bounds__(kGatThreads) k_gat_bwd(const GatArgs a) {
   float* dZ = Pd + N * NP;               // [N][NP]  dP, then dz
   float* dos = dZ + N * NP;              // STAGE: [N][FP] dO
   unsigned char* zpos = reinterpret_cast<unsigned char*>(dos + (STAGE ? N * FP : 0));
+  unsigned char* nzr = zpos + N * N;
+  unsigned char* nzc = nzr + N * N;
+  int* cnt = reinterpret_cast<int*>(zpos + ((3 * N * N + 3) & ~3));
   const size_t g = blockIdx.x;
   const float *Wg = a.Wh + g * N * F, *og = a.out + g * N * F, *dg = a.dout + g * N * F;
   for (int e = tid; e < N * F; e += kGatThreads) {
@@ -119,6 +151,7 @@ __global__ void __launch_bounds__(kGatThreads) k_gat_bwd(const GatArgs a) {
   }
   // dO = dout * outer-ReLU slope; sign(out) = sign(Pd Wh) for slope > 0
   auto dO = [&](int i, int f) { return STAGE ? dos[i * FP + f] : dg[i * F + f] * (og[i * F + f] > 0.f ? 1.f : a.slope); };
+  gat_lists(a, g, nzr, nzc, cnt);
   __syncthreads();
   gat_scores(a, g, whs, FP, s, t, P, Pd, zpos);
   const float ksc = a.pdrop > 0.f ? 1.f / (1.f - a.pdrop) : 1.f;
@@ -172,9 +205,9 @@ __global__ void __launch_bounds__(kGatThreads) k_gat_bwd(const GatArgs a) {
   for (int e = tid; e < N * F; e += kGatThreads) {
     const int j = e / F, f = e - j * F;
     float acc = fmaf(s[j], a.aw[f], t[j] * a.aw[F + f]);
-    for (int i = 0; i < N; ++i) {
-      const float p = Pd[i * NP + j];
-      if (p != 0.f) acc = fmaf(p, dO(i, f), acc);
+    for (int q = 0; q < cnt[N + j]; ++q) {
+      const int i = nzc[j * N + q];
+      acc = fmaf(Pd[i * NP + j], dO(i, f), acc);
     }
     dWg[e] = acc;
   }
@@ -194,11 +227,12 @@ __global__ void __launch_bounds__(kGatThreads) k_gat_bwd(const GatArgs a) {
 size_t gat_smem(int N, int F, bool bwd, bool stage = false) {
   const size_t NP = N + 1, FP = F + 1;
   size_t fl = N * FP + 2 * N + (bwd ? 3 : 2) * N * NP + (stage ? N * FP : 0);
-  return fl * 4 + (size_t)N * N + 16;
+  return fl * 4 + 3 * (size_t)N * N + 8 * (size_t)N + 32;          // + z > 0 flags, row / column non-zero lists, counts
 }
 
 int gat_check(const GatArgs& a, int G, bool bwd) {
   if (G < 1 || a.N < 1 || a.F < 1) return set_err(STG_ERR_INVALID, "gat: non-positive dimension");
+  if (a.N > 256) return set_err(STG_ERR_UNSUPPORTED, "gat: %d nodes per graph (node lists are 8-bit)", a.N);
   if (!a.Wh || !a.aw || !a.ab || !a.adj) return set_err(STG_ERR_INVALID, "gat: null pointer");
   if (a.pdrop < 0.f || a.pdrop >= 1.f) return set_err(STG_ERR_INVALID, "gat: dropout must be in [0,1)");
   if (a.slope <= 0.f) return set_err(STG_ERR_INVALID, "gat: the output leaky_relu slope must be positive");
