@@ -79,6 +79,15 @@ class FlatParams:
             p.grad = None
         self.bind_grads()
 
+    def check_bound(self) -> None:
+        """The parameters must still be views of the flat buffer: `module.to(...)` / `load_state_dict(assign=True)` after
+        flattening re-allocates them, and the kernel would then update a buffer nobody reads."""
+        base = self.param.data_ptr()
+        for i in (0, len(self.params) - 1):          # a moved module re-allocates every parameter: two probes are enough
+            if self.params[i].data_ptr() != base + 4 * self.offsets[i]:
+                raise RuntimeError("a parameter is no longer a view of the flat buffer (module moved or re-assigned after "
+                                   "use_flat_optimizer / attach_data_parallel): build the flat optimizer again")
+
     def gather_stray_grads(self) -> None:
         """autograd may have replaced a .grad view by a fresh tensor (first accumulation into None): copy it back."""
         for p, off in zip(self.params, self.offsets):
@@ -118,6 +127,7 @@ class FlatAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         fl, g = self.flat, self.param_groups[0]
+        fl.check_bound()
         fl.gather_stray_grads()
         lib = _lib.load()
         with torch.cuda.device(fl.param.device):

@@ -45,6 +45,10 @@ def test_used_parameters_and_flat_views_cpu():
     used[0].grad = torch.ones_like(used[0])                       # a replaced .grad is gathered back
     fl.gather_stray_grads()
     assert torch.equal(fl.grad[:used[0].numel()], torch.ones(used[0].numel()))
+    fl.check_bound()
+    m.double()                                                    # re-allocates the parameters: the flat views are gone
+    with pytest.raises(RuntimeError):
+        fl.check_bound()
 
 
 def _st_gcn(dev):
