@@ -253,8 +253,8 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = model_cfg(args.workload)
-    B = args.batch
-    ms, done, threads = cpu_reference_steps(cfg, B, args.steps, args.warmup)
+    B = args.batch * max(1, args.gpus)          # the native arm's GLOBAL batch at this N (weak scaling: per-GPU batch fixed)
+    ms, done, threads = cpu_reference_steps(cfg, B, args.steps, args.warmup, budget_s=150.0)   # bounded: a few minutes
     val = B / (ms / 1e3)
     sample = f"{done} update steps of B={B} ({args.workload}) on {threads} host threads"
     line = {
@@ -262,7 +262,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][1]}", "global_batch": B,
-                   "step": "fwd+mse+bwd+adam", "device": "cpu"},
+                   "per_gpu_batch": args.batch, "step": "fwd+mse+bwd+adam", "device": "cpu"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
