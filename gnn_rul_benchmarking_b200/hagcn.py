@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .primitives import cosine_distance, graph_matmul
+from .primitives import cosine_distance, graph_matmul, tall_linear
 from .rnn import LSTM
 
 
@@ -27,7 +27,9 @@ class GINLayer(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(input_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, hidden_dim))
 
     def forward(self, x, adj):
-        return self.mlp(graph_matmul(adj, x) + (1 + self.eps) * x)
+        h = graph_matmul(adj, x) + (1 + self.eps) * x
+        h = F.relu(tall_linear(h, self.mlp[0].weight, self.mlp[0].bias))        # split-K weight gradients (bs*tlen*N rows)
+        return tall_linear(h, self.mlp[2].weight, self.mlp[2].bias)
 
 
 class Bi_LSTM_Standard(nn.Module):
@@ -71,9 +73,10 @@ class SAGPool(nn.Module):
 
     def forward(self, X, A):
         AX = graph_matmul(A, X)                       # the reference computes bmm(A, X) twice; once is enough
-        x_out = F.leaky_relu(self.model(AX))
-        P = torch.softmax(self.mlp(X), dim=1).squeeze()
-        score = torch.softmax(self.rank(AX), 1).squeeze()
+        x_out = F.leaky_relu(tall_linear(AX, self.model.weight, self.model.bias))
+        hm = F.relu(tall_linear(X, self.mlp[0].weight, self.mlp[0].bias))
+        P = torch.softmax(tall_linear(hm, self.mlp[2].weight, self.mlp[2].bias), dim=1).squeeze()
+        score = torch.softmax(tall_linear(AX, self.rank.weight, self.rank.bias), 1).squeeze()
         kl_div = F.kl_div(P.log(), score, reduction='batchmean')
         _, idx = torch.sort(score, descending=True, dim=1)
         topk = idx[:, :self.n]
